@@ -1,0 +1,84 @@
+"""ctypes binding of libarflow_b200.so — the only door between the Python shim and the kernels.
+
+There is no CPU fallback and no alternative backend: if the library is missing, or a tensor is not
+a contiguous fp32 CUDA tensor, the call raises.  Non-zero return codes of the C-ABI become
+RuntimeError (the reference raises AT_ERROR("CUDA call failed"), correlation_cuda.cc:81-83).
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libarflow_b200.so")
+
+c_int, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+_P = c_void_p  # device pointers travel as void*
+
+# name -> argument types; every function returns int unless listed in _RESTYPES.
+PROTOTYPES = {
+    "arf_version": [],
+    "arf_error_string": [c_int],
+    "arf_corr_out_dims": [c_int] * 7 + [ctypes.POINTER(c_int)] * 3,
+    "arf_corr_fwd": [_P, _P, _P] + [c_int] * 9 + [_P],
+    "arf_corr_bwd": [_P, _P, _P, _P, _P] + [c_int] * 9 + [_P],
+    "arf_warp_fwd": [_P, _P, _P] + [c_int] * 6 + [c_float, c_float] + [c_int] * 4 + [_P],
+    "arf_warp_bwd": [_P, _P, _P, _P, _P] + [c_int] * 6 + [c_float, c_float] + [c_int] * 4 + [_P],
+}
+_RESTYPES = {"arf_error_string": ctypes.c_char_p}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and attach prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "arflow_b200: %s is missing — run `python -m arflow_b200.build` (nvcc, sm_100a). "
+            "There is no CPU or PyTorch fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_int)
+    _lib = lib
+    return lib
+
+
+def error_string(code):
+    return load().arf_error_string(int(code)).decode()
+
+
+def check(code, what):
+    if code != 0:
+        if code == -2:
+            raise NotImplementedError("arflow_b200.%s: %s" % (what, error_string(code)))
+        raise RuntimeError("arflow_b200.%s failed: %s (code %d)" % (what, error_string(code), code))
+
+
+def dev_ptr(t, name="tensor", allow_none=False):
+    """Raw device pointer of a contiguous fp32 CUDA tensor (no silent copies, no CPU path)."""
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError("arflow_b200: %s is None" % name)
+    if not t.is_cuda:
+        raise RuntimeError("arflow_b200: %s must be a CUDA tensor (no CPU fallback exists)" % name)
+    if t.dtype != torch.float32:
+        raise TypeError("arflow_b200: %s must be float32, got %s" % (name, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("arflow_b200: %s must be contiguous" % name)
+    return t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point on the current stream and raise on failure."""
+    rc = getattr(load(), name)(*args)
+    check(rc, name)

@@ -1,0 +1,100 @@
+/*
+ * arflow_b200 — C-ABI boundary of the B200-native unsupervised-flow hot path.
+ *
+ * Every entry point takes raw DEVICE pointers (fp32, contiguous NCHW unless stated), explicit
+ * sizes, and the CUDA stream to launch on (a cudaStream_t passed as void*).  Functions never
+ * allocate, never synchronise and never throw; outputs and workspaces are allocated by the
+ * caller.  Return value: 0 = ok, <0 = argument error (ARF_E*), >0 = cudaError_t of the launch.
+ * The current CUDA device/context of the calling thread is used (the Python shim calls inside
+ * torch's device guard, like the reference does with torch.cuda.device_of, correlation.py:21).
+ *
+ * Reference interfaces replaced (paths relative to deu439/ARFlow):
+ *   arf_corr_*      correlation_cuda.forward/backward  models/correlation_package/correlation_cuda.cc:10-16,89-96,169-172
+ *                   Correlation.forward (native)       models/correlation_native.py:13-23
+ *                   compute_cost_volume                models/uflow_model.py:53-92
+ *   arf_warp_*      flow_warp -> F.grid_sample         utils/warp_utils.py:83-90
+ *                   resample  -> F.grid_sample         utils/uflow_utils.py:53-77
+ *   arf_resampler_* resampler_with_unstacked_warp      utils/uflow_resampler.py:155-241
+ *   arf_range_map   compute_range_map                  utils/uflow_utils.py:80-160, utils/warp_utils.py:158-239
+ *   arf_corr_map    get_corresponding_map              utils/warp_utils.py:26-80
+ *   arf_mask_*      mask_invalid / border_mask         utils/uflow_utils.py:35-50, utils/warp_utils.py:119-134
+ *   arf_occ_bidir   get_occu_mask_bidirection          utils/warp_utils.py:93-100
+ *   arf_census_*    census_loss(_no_penalty), TernaryLoss   utils/uflow_utils.py:241-306, losses/loss_blocks.py:12-62
+ *   arf_ssim_*      ssim_loss, SSIM                    utils/uflow_utils.py:309-334, losses/loss_blocks.py:65-84
+ *   arf_smooth_*    UFlowLoss smoothness block, smooth_loss_no_penalty, smooth_grad_1st/2nd
+ *                                                      losses/uflow_loss.py:58-102, losses/uflow_elbo_loss.py:81-96, losses/loss_blocks.py:87-124
+ *   arf_resize_*    upsample / downsample (bilinear, align_corners=False)   utils/uflow_utils.py:163-204
+ *   arf_stencil_mv_*  matrix_vector_product(_T)_general    utils/triag_solve.py:29-43,59-73
+ *   arf_trisolve    triag_solve_cuda.forward/backward_substitution   utils/triag_solve/triag_solve.cpp:12-36
+ *   arf_inv_diag    triag_solve_cuda.inverse_diagonal  utils/triag_solve/triag_solve.cpp:38-45
+ *   arf_featnorm_*  normalize_features                 models/uflow_model.py:8-50
+ */
+#ifndef ARFLOW_B200_H
+#define ARFLOW_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARF_OK            0
+#define ARF_EINVAL       -1   /* bad shape / parameter / null pointer */
+#define ARF_EUNSUPPORTED -2   /* valid in the reference but not implemented here */
+#define ARF_EWORKSPACE   -3   /* workspace too small */
+
+/* padding modes of the warp (grid_sample padding_mode) */
+#define ARF_PAD_ZEROS      0
+#define ARF_PAD_BORDER     1
+#define ARF_PAD_REFLECTION 2
+/* interpolation modes */
+#define ARF_INTERP_BILINEAR 0
+#define ARF_INTERP_NEAREST  1
+/* what the 2-channel field holds */
+#define ARF_FIELD_FLOW   0    /* displacement: sample at (j + u, i + v)            (flow_warp) */
+#define ARF_FIELD_COORDS 1    /* absolute pixel coordinates (x, y)                 (resample)  */
+
+int         arf_version(void);
+const char* arf_error_string(int code);
+
+/* ---------------------------------------------------------------- correlation ---------- */
+/* Output dims of the cost volume, same arithmetic as correlation_cuda.cc:25-34. */
+int arf_corr_out_dims(int H, int W, int pad, int ks, int md, int s1, int s2,
+                      int* D2, int* oH, int* oW);
+
+/* out[b,(tj+dr)*D+(ti+dr),oy,ox] = 1/(ks*ks*C) * sum_{j,i,c} f1p[b,c,y1+j,x1+i] * f2p[b,c,y1+tj*s2+j,x1+ti*s2+i]
+ * with y1 = oy*s1+md, x1 = ox*s1+md in the zero-padded frame (pad on every side), dr = md/s2, D = 2dr+1
+ * (correlation_cuda_kernel.cu:41-114).  f1,f2: (B,C,H,W); out: (B,D*D,oH,oW). */
+int arf_corr_fwd(const float* f1, const float* f2, float* out,
+                 int B, int C, int H, int W,
+                 int pad, int ks, int md, int s1, int s2, void* stream);
+
+/* gout: (B,D*D,oH,oW); g1,g2: (B,C,H,W), fully overwritten (correlation_cuda_kernel.cu:116-300).
+ * g1 or g2 may be NULL to skip that gradient. */
+int arf_corr_bwd(const float* f1, const float* f2, const float* gout, float* g1, float* g2,
+                 int B, int C, int H, int W,
+                 int pad, int ks, int md, int s1, int s2, void* stream);
+
+/* ---------------------------------------------------------------- backward warp -------- */
+/* y[b,c,i,j] = interp(x[b,c], X, Y) with, in fp32 and in this order (the reference's normalise ->
+ * grid_sample un-normalise round trip, warp_utils.py:16-23 / uflow_utils.py:72-76):
+ *   px = field==FLOW ? float(j) + f[b,0,i,j] : f[b,0,i,j]      (same for py with i, channel 1)
+ *   gx = 2*px/nW1 - 1,  gy = 2*py/nH1 - 1          nW1,nH1 = normalisation divisors (W-1, H-1, or max(.,1))
+ *   X  = align ? (gx+1)/2*(Ws-1) : ((gx+1)*Ws-1)/2 (ATen grid_sampler_unnormalize)
+ * x: (B,C,Hs,Ws); field: (B,2,Ho,Wo); y: (B,C,Ho,Wo). */
+int arf_warp_fwd(const float* x, const float* field, float* y,
+                 int B, int C, int Hs, int Ws, int Ho, int Wo,
+                 float nW1, float nH1, int field_kind, int interp, int pad_mode, int align_corners,
+                 void* stream);
+
+/* gy: (B,C,Ho,Wo).  gx (B,C,Hs,Ws) may be NULL (source detached, e.g. uflow_loss.py:31,34); when given it
+ * is zero-filled here and accumulated with atomics.  gfield (B,2,Ho,Wo) may be NULL. */
+int arf_warp_bwd(const float* x, const float* field, const float* gy, float* gx, float* gfield,
+                 int B, int C, int Hs, int Ws, int Ho, int Wo,
+                 float nW1, float nH1, int field_kind, int interp, int pad_mode, int align_corners,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARFLOW_B200_H */

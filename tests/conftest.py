@@ -1,0 +1,56 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# parity bars of BASELINE.json's north_star (fp32): values 1e-5, gradients 1e-4, relative to the
+# largest magnitude of the reference tensor (SURVEY §7 "hard parts": relative error is ill-defined
+# where |value| ~ 0).
+RTOL_VALUE = 1e-5
+RTOL_GRAD = 1e-4
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
+        return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def rel_err(a, ref):
+    a = a.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    assert a.shape == ref.shape, (a.shape, ref.shape)
+    scale = ref.abs().max().item()
+    if scale == 0.0:
+        scale = 1.0
+    return (a - ref).abs().max().item() / scale
+
+
+def assert_close(a, ref, rtol, what=""):
+    e = rel_err(a, ref)
+    assert e <= rtol, "%s: max|a-ref|/max|ref| = %.3e > %.1e" % (what, e, rtol)
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import oracle.arflow_oracle as o
+    return o

@@ -1,0 +1,104 @@
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+Each fixture holds seeded float32 inputs and the reference's outputs computed twice: in float64
+("truth", suffix _f64) and in float32 (reference precision, suffix _f32).  tests/ never imports the
+reference; they read these files.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("ARFLOW_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+# easydict is only needed by modules we do not exercise; a 3-line stand-in keeps imports working
+if "easydict" not in sys.modules:
+    m = types.ModuleType("easydict")
+    class EasyDict(dict):
+        __getattr__ = dict.__getitem__
+        __setattr__ = dict.__setitem__
+    m.EasyDict = EasyDict
+    sys.modules["easydict"] = m
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def rnd(gen, *shape, scale=1.0, uniform=False):
+    t = torch.rand(*shape, generator=gen) if uniform else torch.randn(*shape, generator=gen)
+    return (t * scale).float()
+
+
+def both(fn, *inputs, grads=None):
+    """Run fn on float64 and float32 copies; returns {name_f64/f32: ndarray}.  If `grads` is given
+    (indices of inputs to differentiate), also returns d(sum(out * w))/d(input) for a fixed w."""
+    res = {}
+    for tag, dt in (("f64", torch.float64), ("f32", torch.float32)):
+        ins = [i.to(dt).clone().requires_grad_(grads is not None and k in grads) if torch.is_tensor(i) else i
+               for k, i in enumerate(inputs)]
+        out = fn(*ins)
+        outs = out if isinstance(out, (tuple, list)) else (out,)
+        for k, o in enumerate(outs):
+            res["out%d_%s" % (k, tag)] = o.detach().numpy()
+        if grads is not None:
+            g = torch.Generator().manual_seed(1234)
+            loss = 0
+            for o in outs:
+                if o.requires_grad:
+                    w = torch.randn(o.shape, generator=g).to(dt)
+                    loss = loss + (o * w).sum()
+            gs = torch.autograd.grad(loss, [ins[k] for k in grads], allow_unused=True)
+            for k, gk in zip(grads, gs):
+                if gk is not None:
+                    res["grad%d_%s" % (k, tag)] = gk.numpy()
+    return res
+
+
+def save(name, inputs, res):
+    d = {"in%d" % k: (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in enumerate(inputs)}
+    d.update(res)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print("%-28s %6.1f KB" % (name, os.path.getsize(os.path.join(OUT, name + ".npz")) / 1024))
+
+
+def main():
+    gen = torch.Generator().manual_seed(0)
+
+    # ---- correlation: correlation_native.Correlation == uflow_model.compute_cost_volume ----
+    from models.correlation_native import Correlation
+    from models.uflow_model import compute_cost_volume, normalize_features
+    corr = Correlation(max_displacement=4, kernel_size=1, stride1=1, stride2=1, corr_multiply=1)
+    for name, shape in (("corr_b2c5_9x11", (2, 5, 9, 11)), ("corr_b1c32_12x16", (1, 32, 12, 16)),
+                        ("corr_b1c3_6x40", (1, 3, 6, 40))):
+        f1, f2 = rnd(gen, *shape), rnd(gen, *shape)
+        res = both(lambda a, b: corr(a, b), f1, f2, grads=(0, 1))
+        chk = both(lambda a, b: compute_cost_volume(a, b, 4), f1, f2)
+        assert np.array_equal(res["out0_f64"], chk["out0_f64"])
+        save(name, (f1, f2), res)
+
+    # ---- warp: flow_warp and resample ----
+    from utils.warp_utils import flow_warp
+    from utils import uflow_utils as uu
+    x, flow = rnd(gen, 2, 3, 7, 9), rnd(gen, 2, 2, 7, 9, scale=2.0)
+    for pad in ("zeros", "border", "reflection"):
+        for align in (True, False):
+            res = both(lambda a, f: flow_warp(a, f, pad=pad, align_corners=align), x, flow, grads=(0, 1))
+            save("flow_warp_%s_%d" % (pad, align), (x, flow), res)
+    res = both(lambda a, f: flow_warp(a, f, mode="nearest"), x, flow)
+    save("flow_warp_nearest", (x, flow), res)
+    xs = rnd(gen, 2, 4, 6, 10)   # source size != flow size
+    res = both(lambda a, f: flow_warp(a, f), xs, flow, grads=(0, 1))
+    save("flow_warp_othersize", (xs, flow), res)
+    x, flow = rnd(gen, 2, 5, 8, 12), rnd(gen, 2, 2, 8, 12, scale=3.0)
+    res = both(lambda a, f: uu.resample(a, uu.flow_to_warp(f)), x, flow, grads=(0, 1))
+    save("resample", (x, flow), res)
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    main()

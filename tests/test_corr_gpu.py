@@ -1,0 +1,84 @@
+"""Parity of the correlation kernels with the oracle / golden fixtures (B200, through the C-ABI)."""
+import pytest
+import torch
+
+from conftest import RTOL_GRAD, RTOL_VALUE, assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(f1, f2, w, **kw):
+    from arflow_b200.correlation import Correlation
+    f1 = f1.cuda().requires_grad_(True)
+    f2 = f2.cuda().requires_grad_(True)
+    out = Correlation(**kw)(f1, f2)
+    g1, g2 = torch.autograd.grad((out * w.cuda().float()).sum(), [f1, f2])
+    return out, g1, g2
+
+
+@pytest.mark.parametrize("name", ["corr_b2c5_9x11", "corr_b1c32_12x16", "corr_b1c3_6x40"])
+def test_golden(name):
+    g = load_golden(name)
+    w = torch.randn(g["out0_f64"].shape, generator=torch.Generator().manual_seed(1234))
+    out, g1, g2 = _run(g["in0"], g["in1"], w, pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1)
+    assert_close(out, g["out0_f64"], RTOL_VALUE, "cost volume")
+    assert_close(g1, g["grad0_f64"], RTOL_GRAD, "grad f1")
+    assert_close(g2, g["grad1_f64"], RTOL_GRAD, "grad f2")
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 24, 32), (1, 196, 6, 8), (3, 7, 33, 65), (1, 64, 48, 64), (2, 96, 12, 20)])
+def test_fast_path_vs_oracle(oracle, shape):
+    gen = torch.Generator().manual_seed(sum(shape))
+    f1, f2 = torch.randn(shape, generator=gen), torch.randn(shape, generator=gen)
+    ref = oracle.corr_fwd_c(f1, f2)
+    w = torch.randn(ref.shape, generator=gen)
+    r1, r2 = oracle.corr_bwd_c(f1, f2, w)
+    out, g1, g2 = _run(f1, f2, w, pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1)
+    assert_close(out, ref, RTOL_VALUE, "cost volume")
+    assert_close(g1, r1, RTOL_GRAD, "grad f1")
+    assert_close(g2, r2, RTOL_GRAD, "grad f2")
+
+
+@pytest.mark.parametrize("geom", [(3, 1, 3, 1, 1), (4, 3, 4, 1, 1), (6, 3, 4, 2, 2), (20, 1, 20, 1, 2), (2, 1, 4, 1, 1),
+                                  (4, 1, 4, 2, 1), (5, 5, 3, 3, 1)])
+def test_general_geometry_vs_oracle(oracle, geom):
+    pad, ks, md, s1, s2 = geom
+    gen = torch.Generator().manual_seed(pad * 100 + ks * 10 + md)
+    shape = (2, 6, 26, 30) if md < 20 else (1, 4, 30, 34)
+    f1, f2 = torch.randn(shape, generator=gen), torch.randn(shape, generator=gen)
+    ref = oracle.corr_fwd_c(f1, f2, pad, ks, md, s1, s2)
+    w = torch.randn(ref.shape, generator=gen)
+    r1, r2 = oracle.corr_bwd_c(f1, f2, w, pad, ks, md, s1, s2)
+    out, g1, g2 = _run(f1, f2, w, pad_size=pad, kernel_size=ks, max_displacement=md, stride1=s1, stride2=s2)
+    assert_close(out, ref, RTOL_VALUE, "cost volume")
+    assert_close(g1, r1, RTOL_GRAD, "grad f1")
+    assert_close(g2, r2, RTOL_GRAD, "grad f2")
+
+
+def test_native_style_constructor_and_cost_volume_api(oracle):
+    from arflow_b200.correlation import Correlation, compute_cost_volume
+    gen = torch.Generator().manual_seed(7)
+    f1, f2 = torch.randn(2, 32, 20, 28, generator=gen), torch.randn(2, 32, 20, 28, generator=gen)
+    ref = oracle.cost_volume(f1.double(), f2.double())
+    a = Correlation(max_displacement=4, kernel_size=1, stride1=1, stride2=1, corr_multiply=1)(f1.cuda(), f2.cuda())
+    b = compute_cost_volume(f1.cuda(), f2.cuda(), 4)
+    assert_close(a, ref, RTOL_VALUE)
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        compute_cost_volume(f1.cuda()[:, :, :4], f2.cuda()[:, :, :4], 4)
+
+
+def test_linearity_at_full_size():
+    """Size-independent property at the config-2 L1 shape: corr(a*f1, f2) == a*corr(f1, f2), and the
+    zero-displacement plane equals mean_c(f1*f2)."""
+    from arflow_b200.correlation import compute_cost_volume
+    gen = torch.Generator().manual_seed(11)
+    f1 = torch.randn(8, 32, 96, 128, generator=gen).cuda()
+    f2 = torch.randn(8, 32, 96, 128, generator=gen).cuda()
+    cv = compute_cost_volume(f1, f2, 4)
+    assert_close(compute_cost_volume(2.0 * f1, f2, 4), 2.0 * cv, 1e-6)
+    assert_close(cv[:, 40], (f1 * f2).mean(1), RTOL_VALUE)
+    # shifting f2 by one pixel moves the planes: plane(dy,dx) of shifted == plane(dy,dx+1) of original (interior)
+    f2s = torch.roll(f2, shifts=1, dims=3)
+    cvs = compute_cost_volume(f1, f2s, 4)
+    assert_close(cvs[:, 41, :, 8:-8], cv[:, 40, :, 8:-8], RTOL_VALUE)

@@ -1,0 +1,101 @@
+"""Kernel micro-benchmarks (config 5 of BASELINE.json): CUDA-event timings of the C-ABI calls,
+algorithmic GB/s (SURVEY §8d byte counts) and fraction of the measured HBM peak.
+
+    python tools/microbench.py [corr|warp|all] [--csv gpurun_out/micro.csv]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+def time_fn(fn, iters=20, warmup=5, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) * 1e-3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", nargs="?", default="all")
+    ap.add_argument("--csv", default=None)
+    args = ap.parse_args()
+    from arflow_b200 import _lib
+    from arflow_b200.correlation import corr_out_dims
+    lib = _lib.load()
+    hbm, src = peaks()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")  # 256 MB > 126 MB L2
+    st = torch.cuda.current_stream().cuda_stream
+    rows = []
+
+    def report(kind, shape, bytes_alg, flops, med, best):
+        gbs = bytes_alg / med / 1e9
+        rows.append((kind, "x".join(map(str, shape)), med * 1e6, best * 1e6, gbs, gbs / hbm, flops / med / 1e12))
+        print("%-10s %-18s med %8.1f us  best %8.1f us  %8.1f GB/s  %5.1f%% HBM(%s)  %6.2f TFLOP/s"
+              % (kind, rows[-1][1], med * 1e6, best * 1e6, gbs, 100 * gbs / hbm, src, flops / med / 1e12), flush=True)
+
+    shapes = [(8, 32, 96, 128), (64, 32, 96, 128), (8, 32, 48, 64), (8, 32, 24, 32), (8, 32, 12, 16),
+              (32, 32, 112, 256), (16, 64, 48, 64), (16, 96, 24, 32), (16, 128, 12, 16), (16, 196, 6, 8),
+              (1, 32, 96, 160), (1, 192, 6, 10)]
+    if args.what in ("corr", "all"):
+        for (B, C, H, W) in shapes:
+            f1 = torch.randn(B, C, H, W, device="cuda")
+            f2 = torch.randn(B, C, H, W, device="cuda")
+            out = torch.empty(B, 81, H, W, device="cuda")
+            go = torch.randn(B, 81, H, W, device="cuda")
+            g1, g2 = torch.empty_like(f1), torch.empty_like(f2)
+            fwd = lambda: lib.arf_corr_fwd(f1.data_ptr(), f2.data_ptr(), out.data_ptr(), B, C, H, W, 4, 1, 4, 1, 1, st)
+            bwd = lambda: lib.arf_corr_bwd(f1.data_ptr(), f2.data_ptr(), go.data_ptr(), g1.data_ptr(), g2.data_ptr(),
+                                           B, C, H, W, 4, 1, 4, 1, 1, st)
+            px = B * H * W
+            report("corr_fwd", (B, C, H, W), px * (8 * C + 324), px * C * 162, *time_fn(fwd, flush=flush))
+            report("corr_bwd", (B, C, H, W), px * (16 * C + 324), px * C * 324, *time_fn(bwd, flush=flush))
+    if args.what in ("warp", "all"):
+        for (B, C, H, W) in shapes[:8] + [(8, 3, 384, 512), (32, 3, 448, 1024)]:
+            x = torch.randn(B, C, H, W, device="cuda")
+            fl = torch.randn(B, 2, H, W, device="cuda") * 2
+            y = torch.empty_like(x)
+            gy = torch.randn_like(x)
+            gx, gf = torch.empty_like(x), torch.empty_like(fl)
+            a = (B, C, H, W, H, W, float(W - 1), float(H - 1), 0, 0, 0, 1)
+            fwd = lambda: lib.arf_warp_fwd(x.data_ptr(), fl.data_ptr(), y.data_ptr(), *a, st)
+            bwd = lambda: lib.arf_warp_bwd(x.data_ptr(), fl.data_ptr(), gy.data_ptr(), gx.data_ptr(), gf.data_ptr(), *a, st)
+            bwf = lambda: lib.arf_warp_bwd(x.data_ptr(), fl.data_ptr(), gy.data_ptr(), None, gf.data_ptr(), *a, st)
+            px = B * H * W
+            report("warp_fwd", (B, C, H, W), px * (8 * C + 8), px * C * 8, *time_fn(fwd, flush=flush))
+            report("warp_bwd", (B, C, H, W), px * (12 * C + 16), px * C * 16, *time_fn(bwd, flush=flush))
+            report("warp_bwdF", (B, C, H, W), px * (8 * C + 16), px * C * 16, *time_fn(bwf, flush=flush))
+    if args.csv:
+        os.makedirs(os.path.dirname(args.csv), exist_ok=True)
+        with open(args.csv, "w") as f:
+            f.write("kernel,shape,median_us,best_us,alg_GBps,frac_hbm,TFLOPs\n")
+            for r in rows:
+                f.write("%s,%s,%.2f,%.2f,%.1f,%.4f,%.3f\n" % r)
+
+
+if __name__ == "__main__":
+    main()
