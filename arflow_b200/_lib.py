@@ -19,6 +19,7 @@ _P = c_void_p  # device pointers travel as void*
 PROTOTYPES = {
     "arf_version": [],
     "arf_error_string": [c_int],
+    "arf_debug_set": [c_int, c_int],
     "arf_corr_out_dims": [c_int] * 7 + [ctypes.POINTER(c_int)] * 3,
     "arf_corr_fwd": [_P, _P, _P] + [c_int] * 9 + [_P],
     "arf_corr_bwd": [_P, _P, _P, _P, _P] + [c_int] * 9 + [_P],

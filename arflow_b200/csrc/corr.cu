@@ -12,6 +12,8 @@
 //   through an NHWC staging copy (the reference's channels_first pass, .cu:15-39, is gone):
 //   tiles are staged straight from NCHW, zero padding is produced while staging.
 #include "common.cuh"
+#include "tma.cuh"
+#include <string.h>
 
 namespace {
 
@@ -94,78 +96,356 @@ constexpr int kMD = 4;
 constexpr int kD = 2 * kMD + 1;    // 9
 constexpr int kHW = kTW + 2 * kMD; // 40 halo width
 constexpr int kHH = kTH + 2 * kMD; // 16 halo height
-constexpr int kCc = 8;             // channels staged per chunk
-constexpr int kFwdThreads = 32 * kD;
+constexpr int kCc = 8;             // channels per pipeline stage
+constexpr int kConsumerWarps = kD;                    // warp w <-> dx = w-4
+constexpr int kFwdThreads = 32 * (kConsumerWarps + 1);  // + 1 producer warp
 
-__global__ void __launch_bounds__(kFwdThreads, 2)
-corr_fwd_md4(const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ out,
-             int C, int H, int W, float inv_c, int use_div) {
-    __shared__ float s1[kCc][kTH][kTW];
-    __shared__ float s2[kCc][kHH][kHW];
+struct __align__(128) FwdStage {
+    float s1[kCc][kTH][kTW];   // f1 tile                    8 KB
+    float s2[kCc][kHH][kHW];   // f2 tile with 4-px halo    20 KB
+};
+constexpr uint32_t kFwdStageBytes = sizeof(FwdStage);
+constexpr size_t fwd_smem(int stages) { return stages * sizeof(FwdStage) + 2 * stages * sizeof(uint64_t); }
+
+// Persistent, warp-specialised: warp 9 streams (f1 tile, f2 halo tile) channel chunks through a
+// kStages-deep shared-memory ring (TMA with hardware zero fill when kTma, else zero-filling
+// cp.async), warps 0..8 consume.  The ring keeps running across tile boundaries, so the loads of
+// the next tile overlap the 72 output stores per thread of the current one.
+template <bool kTma, int kStg, int kMinBlocks, int kUnroll>
+__global__ void __launch_bounds__(kFwdThreads, kMinBlocks)
+corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
+             const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ out,
+             int B, int C, int H, int W, int tiles_x, int tiles_y, float inv_c) {
+    constexpr int kStages = kStg;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FwdStage* stg = reinterpret_cast<FwdStage*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(FwdStage));
+    uint64_t* empty = full + kStages;
 
     const int lane = threadIdx.x & 31;
-    const int wdx = threadIdx.x >> 5;  // 0..8  -> dx = wdx-4
-    const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            arf::mbar_init(&full[s], kTma ? 1 : 32);
+            arf::mbar_init(&empty[s], kConsumerWarps);
+        }
+        arf::mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int ntiles = tiles_x * tiles_y * B;
+    const int nchunks = (C + kCc - 1) / kCc;
     const size_t plane = (size_t)H * W;
-    const float* f1b = f1 + (size_t)b * C * plane;
-    const float* f2b = f2 + (size_t)b * C * plane;
 
-    float acc[kTH][kD];
-#pragma unroll
-    for (int r = 0; r < kTH; ++r)
-#pragma unroll
-        for (int d = 0; d < kD; ++d) acc[r][d] = 0.f;
+    if (warp == kConsumerWarps) {
+        // ------------------------------------------------------------ producer warp
+        if (kTma && lane == 0) {
+            arf::tma_prefetch_desc(&map1);
+            arf::tma_prefetch_desc(&map2);
+        }
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+            const int x0 = tx * kTW, y0 = ty * kTH;
+            for (int ch = 0; ch < nchunks; ++ch, ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                arf::mbar_wait(&empty[s], ph ^ 1);
+                const int c0 = ch * kCc;
+                if (kTma) {
+                    if (lane == 0) {
+                        arf::mbar_arrive_expect_tx(&full[s], kFwdStageBytes);
+                        arf::tma_load_4d(&stg[s].s1[0][0][0], &map1, &full[s], x0, y0, c0, b);
+                        arf::tma_load_4d(&stg[s].s2[0][0][0], &map2, &full[s], x0 - kMD, y0 - kMD, c0, b);
+                    }
+                } else {
+                    const float* f1b = f1 + (size_t)b * C * plane;
+                    const float* f2b = f2 + (size_t)b * C * plane;
+                    for (int e = lane; e < kCc * kTH * kTW; e += 32) {
+                        int rr = (e / kTW) % kTH, cc = e / (kTW * kTH);
+                        int gx = x0 + lane, gy = y0 + rr, gc = c0 + cc;
+                        bool ok = gc < C && gy < H && gx < W;
+                        arf::cp_async_4_zfill(&stg[s].s1[cc][rr][lane],
+                                              ok ? f1b + gc * plane + (size_t)gy * W + gx : f1b, ok);
+                    }
+                    for (int e = lane; e < kCc * kHH * kHW; e += 32) {
+                        int xx = e % kHW, rr = (e / kHW) % kHH, cc = e / (kHW * kHH);
+                        int gx = x0 + xx - kMD, gy = y0 + rr - kMD, gc = c0 + cc;
+                        bool ok = gc < C && gy >= 0 && gy < H && gx >= 0 && gx < W;
+                        arf::cp_async_4_zfill(&stg[s].s2[cc][rr][xx],
+                                              ok ? f2b + gc * plane + (size_t)gy * W + gx : f2b, ok);
+                    }
+                    arf::cp_async_mbar_arrive_noinc(&full[s]);
+                }
+            }
+        }
+        return;
+    }
 
-    for (int c0 = 0; c0 < C; c0 += kCc) {
-        // stage f1 tile
-        for (int e = threadIdx.x; e < kCc * kTH * kTW; e += kFwdThreads) {
-            int xx = e % kTW, rr = (e / kTW) % kTH, cc = e / (kTW * kTH);
-            int gx = x0 + xx, gy = y0 + rr, gc = c0 + cc;
-            float v = 0.f;
-            if (gc < C && gy < H && gx < W) v = __ldg(f1b + gc * plane + (size_t)gy * W + gx);
-            s1[cc][rr][xx] = v;
+    // ---------------------------------------------------------------- consumer warps
+    const int wdx = warp;  // 0..8 -> dx = wdx-4
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+        const int x0 = tx * kTW, y0 = ty * kTH;
+
+        float acc[kTH][kD];
+#pragma unroll
+        for (int r = 0; r < kTH; ++r)
+#pragma unroll
+            for (int d = 0; d < kD; ++d) acc[r][d] = 0.f;
+
+        for (int ch = 0; ch < nchunks; ++ch, ++it) {
+            const int s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            arf::mbar_wait(&full[s], ph);
+            const FwdStage& S = stg[s];
+#pragma unroll kUnroll
+            for (int cc = 0; cc < kCc; ++cc) {
+                float a[kTH], bb[kHH];
+#pragma unroll
+                for (int r = 0; r < kTH; ++r) a[r] = S.s1[cc][r][lane];
+#pragma unroll
+                for (int k = 0; k < kHH; ++k) bb[k] = S.s2[cc][k][lane + wdx];
+#pragma unroll
+                for (int r = 0; r < kTH; ++r)
+#pragma unroll
+                    for (int d = 0; d < kD; ++d) acc[r][d] = fmaf(a[r], bb[r + d], acc[r][d]);
+            }
+            __syncwarp();
+            if (lane == 0) arf::mbar_arrive(&empty[s]);
         }
-        // stage f2 halo tile (zero outside the image == the reference's zero padding)
-        for (int e = threadIdx.x; e < kCc * kHH * kHW; e += kFwdThreads) {
-            int xx = e % kHW, rr = (e / kHW) % kHH, cc = e / (kHW * kHH);
-            int gx = x0 + xx - kMD, gy = y0 + rr - kMD, gc = c0 + cc;
-            float v = 0.f;
-            if (gc < C && gy >= 0 && gy < H && gx >= 0 && gx < W)
-                v = __ldg(f2b + gc * plane + (size_t)gy * W + gx);
-            s2[cc][rr][xx] = v;
+
+        // epilogue: 72 coalesced 128-byte row stores per warp; mean over channels = sum * (1/C)
+        const int gx = x0 + lane;
+        float* op = out + ((size_t)b * (kD * kD) + wdx) * plane + (size_t)y0 * W + gx;
+        const size_t dstride = (size_t)kD * plane;
+        if (x0 + kTW <= W && y0 + kTH <= H) {
+#pragma unroll
+            for (int d = 0; d < kD; ++d) {
+#pragma unroll
+                for (int r = 0; r < kTH; ++r) __stcs(op + r * W, acc[r][d] * inv_c);
+                op += dstride;
+            }
+        } else if (gx < W) {
+#pragma unroll
+            for (int d = 0; d < kD; ++d) {
+#pragma unroll
+                for (int r = 0; r < kTH; ++r)
+                    if (y0 + r < H) __stcs(op + r * W, acc[r][d] * inv_c);
+                op += dstride;
+            }
         }
-        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ tiled backward, md=4 -
+// g1[c,y,x] = 1/C sum_{dy,dx} gO[(dy,dx),y,x]       * f2[c,y+dy,x+dx]           (kSecond = false, F = f2)
+// g2[c,y,x] = 1/C sum_{dy,dx} gO[(dy,dx),y-dy,x-dx] * f1[c,y-dy,x-dx]           (kSecond = true,  F = f1)
+// Both are gathers (no atomics, nothing to zero-fill).  Work item = (32 x 16 pixel tile, 32 channels).
+// 8 consumer warps = 2 row groups (8 rows each) x 4 channel groups (8 channels each); lane <-> x.
+// For each of the 9 horizontal displacements a warp pulls the 8 rows x 9 vertical displacements of gO
+// for its column into registers (from a TMA-streamed "slab" = the 9 planes of that dx) and reuses them
+// for its 8 channels: per channel 16 LDS (halo column of F) feed 72 FFMA into 8 accumulators.
+constexpr int kBTH = 16;                 // tile height of the backward
+constexpr int kBHH = kBTH + 2 * kMD;     // 24
+constexpr int kBC = 32;                  // channels per work item
+constexpr int kBCg = 8;                  // channels per warp
+constexpr int kBStages = 3;              // slab ring depth
+constexpr int kBConsumers = 2 * (kBC / kBCg);          // 8 warps
+constexpr int kBwdThreads = 32 * (kBConsumers + 1);    // + producer warp
+constexpr int kNFBar = kBC / kBCg;                     // one "F arrived" barrier per channel group
+
+template <bool kSecond>
+struct BwdSmem {
+    static constexpr int kSlabRows = kSecond ? kBHH : kBTH;
+    float F[kBC][kBHH][kHW];                    // 122 880 B : halo tile of the other feature map
+    float slab[kBStages][kD][kSlabRows][kTW];   // 3 x 18 432 B (first) / 3 x 27 648 B (second)
+    uint64_t f_full[kNFBar], f_empty, s_full[kBStages], s_empty[kBStages];
+};
+
+template <bool kSecond, bool kTma>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+corr_bwd_md4(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapG,
+             const float* __restrict__ Fsrc, const float* __restrict__ gout, float* __restrict__ gin,
+             int B, int C, int H, int W, int tiles_x, int tiles_y, int nsuper, float inv_c) {
+    using Smem = BwdSmem<kSecond>;
+    constexpr int kSlabRows = Smem::kSlabRows;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kNFBar; ++i) arf::mbar_init(&sm.f_full[i], kTma ? 1 : 32);
+        arf::mbar_init(&sm.f_empty, kBConsumers);
+        for (int s = 0; s < kBStages; ++s) {
+            arf::mbar_init(&sm.s_full[s], kTma ? 1 : 32);
+            arf::mbar_init(&sm.s_empty[s], kBConsumers);
+        }
+        arf::mbar_fence_init();
+    }
+    __syncthreads();
+
+    const long long nitems = (long long)tiles_x * tiles_y * B * nsuper;
+    const size_t plane = (size_t)H * W;
+
+    if (warp == kBConsumers) {
+        // ------------------------------------------------------------ producer warp
+        if (kTma && lane == 0) {
+            arf::tma_prefetch_desc(&mapF);
+            arf::tma_prefetch_desc(&mapG);
+        }
+        uint32_t it = 0, item = 0;
+        for (long long t = blockIdx.x; t < nitems; t += gridDim.x, ++item) {
+            const int cs = t % nsuper;
+            long long tt = t / nsuper;
+            const int tx = tt % tiles_x, ty = (tt / tiles_x) % tiles_y, b = tt / ((long long)tiles_x * tiles_y);
+            const int x0 = tx * kTW, y0 = ty * kBTH, c0 = cs * kBC;
+            arf::mbar_wait(&sm.f_empty, (item & 1) ^ 1);
+            if (kTma) {
+                if (lane == 0) {
+                    for (int gch = 0; gch < kNFBar; ++gch) {
+                        arf::mbar_arrive_expect_tx(&sm.f_full[gch], kBCg * kBHH * kHW * 4);
+                        arf::tma_load_4d(&sm.F[gch * kBCg][0][0], &mapF, &sm.f_full[gch], x0 - kMD, y0 - kMD,
+                                         c0 + gch * kBCg, b);
+                    }
+                }
+            } else {
+                const float* fb = Fsrc + (size_t)b * C * plane;
+                for (int gch = 0; gch < kNFBar; ++gch) {
+                    for (int e = lane; e < kBCg * kBHH * kHW; e += 32) {
+                        int xx = e % kHW, rr = (e / kHW) % kBHH, cc = gch * kBCg + e / (kHW * kBHH);
+                        int gx = x0 + xx - kMD, gy = y0 + rr - kMD, gc = c0 + cc;
+                        bool ok = gc < C && gy >= 0 && gy < H && gx >= 0 && gx < W;
+                        arf::cp_async_4_zfill(&sm.F[cc][rr][xx], ok ? fb + gc * plane + (size_t)gy * W + gx : fb, ok);
+                    }
+                    arf::cp_async_mbar_arrive_noinc(&sm.f_full[gch]);
+                }
+            }
+            for (int dx = 0; dx < kD; ++dx, ++it) {
+                const int s = it % kBStages;
+                arf::mbar_wait(&sm.s_empty[s], ((it / kBStages) & 1) ^ 1);
+                // first: rows y0.., columns x0..            second: rows y0-4.., columns shifted by -(dx-4)
+                const int sx = kSecond ? x0 - (dx - kMD) : x0;
+                const int sy = kSecond ? y0 - kMD : y0;
+                if (kTma) {
+                    if (lane == 0) {
+                        arf::mbar_arrive_expect_tx(&sm.s_full[s], kD * kSlabRows * kTW * 4);
+                        arf::tma_load_5d(&sm.slab[s][0][0][0], &mapG, &sm.s_full[s], sx, sy, dx, 0, b);
+                    }
+                } else {
+                    const float* gb = gout + (size_t)b * kD * kD * plane;
+                    for (int e = lane; e < kD * kSlabRows * kTW; e += 32) {
+                        int rr = (e / kTW) % kSlabRows, dy = e / (kTW * kSlabRows);
+                        int gx = sx + lane, gy = sy + rr;
+                        bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+                        arf::cp_async_4_zfill(&sm.slab[s][dy][rr][lane],
+                                              ok ? gb + (size_t)(dy * kD + dx) * plane + (size_t)gy * W + gx : gb, ok);
+                    }
+                    arf::cp_async_mbar_arrive_noinc(&sm.s_full[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumer warps
+    const int rg = warp / kNFBar;        // row group: rows rg*8 .. rg*8+7 of the tile
+    const int cgp = warp % kNFBar;       // channel group: channels cgp*8 .. cgp*8+7 of the work item
+    const int r0 = rg * kTH;
+    uint32_t it = 0, item = 0;
+    for (long long t = blockIdx.x; t < nitems; t += gridDim.x, ++item) {
+        const int cs = t % nsuper;
+        long long tt = t / nsuper;
+        const int tx = tt % tiles_x, ty = (tt / tiles_x) % tiles_y, b = tt / ((long long)tiles_x * tiles_y);
+        const int x0 = tx * kTW, y0 = ty * kBTH, c0 = cs * kBC;
+
+        float o[kBCg][kTH];
+#pragma unroll
+        for (int c = 0; c < kBCg; ++c)
+#pragma unroll
+            for (int r = 0; r < kTH; ++r) o[c][r] = 0.f;
+
+        arf::mbar_wait(&sm.f_full[cgp], item & 1);
 #pragma unroll 1
-        for (int cc = 0; cc < kCc; ++cc) {
-            float a[kTH], bb[kHH];
-#pragma unroll
-            for (int r = 0; r < kTH; ++r) a[r] = s1[cc][r][lane];
-#pragma unroll
-            for (int k = 0; k < kHH; ++k) bb[k] = s2[cc][k][lane + wdx];
+        for (int dx = 0; dx < kD; ++dx, ++it) {
+            const int s = it % kBStages;
+            arf::mbar_wait(&sm.s_full[s], (it / kBStages) & 1);
+            float g[kTH][kD];
 #pragma unroll
             for (int r = 0; r < kTH; ++r)
 #pragma unroll
-                for (int d = 0; d < kD; ++d) acc[r][d] = fmaf(a[r], bb[r + d], acc[r][d]);
+                for (int d = 0; d < kD; ++d)
+                    g[r][d] = kSecond ? sm.slab[s][d][r0 + r + 2 * kMD - d][lane] : sm.slab[s][d][r0 + r][lane];
+            __syncwarp();
+            if (lane == 0) arf::mbar_arrive(&sm.s_empty[s]);
+            const int col = kSecond ? lane + 2 * kMD - dx : lane + dx;
+#pragma unroll
+            for (int c = 0; c < kBCg; ++c) {
+                float bb[kHH];
+#pragma unroll
+                for (int k = 0; k < kHH; ++k) bb[k] = sm.F[cgp * kBCg + c][r0 + k][col];
+#pragma unroll
+                for (int r = 0; r < kTH; ++r)
+#pragma unroll
+                    for (int d = 0; d < kD; ++d)
+                        o[c][r] = fmaf(g[r][d], kSecond ? bb[r + 2 * kMD - d] : bb[r + d], o[c][r]);
+            }
         }
-        __syncthreads();
-    }
+        __syncwarp();
+        if (lane == 0) arf::mbar_arrive(&sm.f_empty);
 
-    const int gx = x0 + lane;
-    if (gx < W) {
-        float* ob = out + (size_t)b * (kD * kD) * plane;
+        const int gx = x0 + lane;
+        if (gx < W) {
 #pragma unroll
-        for (int d = 0; d < kD; ++d) {
-            float* op = ob + (size_t)(d * kD + wdx) * plane;
+            for (int c = 0; c < kBCg; ++c) {
+                const int gc = c0 + cgp * kBCg + c;
+                if (gc < C) {
+                    float* op = gin + ((size_t)b * C + gc) * plane + (size_t)(y0 + r0) * W + gx;
 #pragma unroll
-            for (int r = 0; r < kTH; ++r) {
-                int gy = y0 + r;
-                if (gy < H) {
-                    float v = use_div ? acc[r][d] / (float)C : acc[r][d] * inv_c;
-                    __stcs(op + (size_t)gy * W + gx, v);
+                    for (int r = 0; r < kTH; ++r)
+                        if (y0 + r0 + r < H) op[(size_t)r * W] = o[c][r] * inv_c;
                 }
             }
         }
     }
+}
+
+template <bool kSecond>
+int launch_bwd_md4(const float* Fsrc, const float* gout, float* gin, int B, int C, int H, int W, bool want_tma,
+                   cudaStream_t st) {
+    const int tiles_x = arf_cdiv(W, kTW), tiles_y = arf_cdiv(H, kBTH), nsuper = arf_cdiv(C, kBC);
+    const long long nitems = (long long)tiles_x * tiles_y * B * nsuper;
+    const int grid = (int)(nitems < ARF_NUM_SMS ? nitems : ARF_NUM_SMS);
+    constexpr int rows = BwdSmem<kSecond>::kSlabRows;
+    CUtensorMap mF, mG;
+    bool tma = want_tma && arf::tma_ok_nchw(Fsrc, W) && arf::tma_ok_nchw(gout, W) &&
+               arf::make_map_nchw(&mF, Fsrc, B, C, H, W, kHW, kBHH, kBCg) &&
+               arf::make_map_costvol(&mG, gout, B, kD, H, W, kTW, rows);
+    const float inv_c = 1.0f / (float)C;
+    const size_t smem = sizeof(BwdSmem<kSecond>);
+    if (tma) {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(corr_bwd_md4<kSecond, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr = true;
+        }
+        corr_bwd_md4<kSecond, true><<<grid, kBwdThreads, smem, st>>>(mF, mG, Fsrc, gout, gin, B, C, H, W, tiles_x,
+                                                                     tiles_y, nsuper, inv_c);
+    } else {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(corr_bwd_md4<kSecond, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr = true;
+        }
+        memset(&mF, 0, sizeof(mF));
+        memset(&mG, 0, sizeof(mG));
+        corr_bwd_md4<kSecond, false><<<grid, kBwdThreads, smem, st>>>(mF, mG, Fsrc, gout, gin, B, C, H, W, tiles_x,
+                                                                      tiles_y, nsuper, inv_c);
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? ARF_OK : (int)e;
 }
 
 int make_geom(CorrGeom& g, int B, int C, int H, int W, int pad, int ks, int md, int s1, int s2) {
@@ -183,11 +463,20 @@ int make_geom(CorrGeom& g, int B, int C, int H, int W, int pad, int ks, int md, 
     return ARF_OK;
 }
 
+int g_variant = 0;       // test hook: kernel variant selection while tuning
+int g_force_no_tma = 0;  // test hook: exercise the cp.async producer on TMA-capable shapes
+
 inline bool is_fast(const CorrGeom& g) {
     return g.ks == 1 && g.s1 == 1 && g.s2 == 1 && g.md == kMD && g.pad == kMD;
 }
 
 }  // namespace
+
+extern "C" int arf_debug_set(int key, int value) {
+    if (key == 0) { g_force_no_tma = value; return ARF_OK; }
+    if (key == 1) { g_variant = value; return ARF_OK; }
+    return ARF_EINVAL;
+}
 
 extern "C" int arf_corr_out_dims(int H, int W, int pad, int ks, int md, int s1, int s2,
                                  int* D2, int* oH, int* oW) {
@@ -207,10 +496,35 @@ extern "C" int arf_corr_fwd(const float* f1, const float* f2, float* out, int B,
     int rc = make_geom(g, B, C, H, W, pad, ks, md, s1, s2);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (is_fast(g) && B <= 65535) {
-        dim3 grid(arf_cdiv(W, kTW), arf_cdiv(H, kTH), B);
-        int pow2 = (C & (C - 1)) == 0;
-        corr_fwd_md4<<<grid, kFwdThreads, 0, st>>>(f1, f2, out, C, H, W, 1.0f / (float)C, !pow2);
+    if (is_fast(g)) {
+        const int tiles_x = arf_cdiv(W, kTW), tiles_y = arf_cdiv(H, kTH);
+        const long long ntiles = (long long)tiles_x * tiles_y * B;
+        if (ntiles > 0x7fffffffLL) return ARF_EINVAL;
+        CUtensorMap m1, m2;
+        bool tma = !g_force_no_tma && arf::tma_ok_nchw(f1, W) && arf::tma_ok_nchw(f2, W) &&
+                   arf::make_map_nchw(&m1, f1, B, C, H, W, kTW, kTH, kCc) &&
+                   arf::make_map_nchw(&m2, f2, B, C, H, W, kHW, kHH, kCc);
+        if (!tma) {
+            memset(&m1, 0, sizeof(m1));
+            memset(&m2, 0, sizeof(m2));
+        }
+        const float inv_c = 1.0f / (float)C;
+#define ARF_LAUNCH_FWD(TMA, STG, MINB, UNR)                                                                  \
+    do {                                                                                                     \
+        auto kern = corr_fwd_md4<TMA, STG, MINB, UNR>;                                                       \
+        static bool attr = false;                                                                            \
+        if (!attr) {                                                                                         \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(STG));     \
+            attr = true;                                                                                     \
+        }                                                                                                    \
+        const int grid = (int)(ntiles < (MINB) * ARF_NUM_SMS ? ntiles : (MINB) * ARF_NUM_SMS);               \
+        kern<<<grid, kFwdThreads, fwd_smem(STG), st>>>(m1, m2, f1, f2, out, B, C, H, W, tiles_x, tiles_y, inv_c); \
+    } while (0)
+        if (!tma) ARF_LAUNCH_FWD(false, 3, 2, 1);
+        else if (g_variant == 1) ARF_LAUNCH_FWD(true, 6, 1, 2);
+        else if (g_variant == 2) ARF_LAUNCH_FWD(true, 6, 1, 1);
+        else ARF_LAUNCH_FWD(true, 3, 2, 1);
+#undef ARF_LAUNCH_FWD
     } else {
         long long total = (long long)B * g.D * g.D * g.oH * g.oW;
         corr_fwd_literal<<<arf_grid_1d(total, 256), 256, 0, st>>>(f1, f2, out, g);
@@ -227,6 +541,17 @@ extern "C" int arf_corr_bwd(const float* f1, const float* f2, const float* gout,
     int rc = make_geom(g, B, C, H, W, pad, ks, md, s1, s2);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (is_fast(g)) {
+        if (g1) {
+            rc = launch_bwd_md4<false>(f2, gout, g1, B, C, H, W, !g_force_no_tma, st);
+            if (rc) return rc;
+        }
+        if (g2) {
+            rc = launch_bwd_md4<true>(f1, gout, g2, B, C, H, W, !g_force_no_tma, st);
+            if (rc) return rc;
+        }
+        return ARF_OK;
+    }
     long long total = (long long)B * C * H * W;
     if (g1) {
         corr_bwd_literal<<<arf_grid_1d(total, 256), 256, 0, st>>>(f2, gout, g1, g, 0);

@@ -56,6 +56,8 @@ extern "C" {
 
 int         arf_version(void);
 const char* arf_error_string(int code);
+/* Test hook. key 0: value != 0 forces the non-TMA (cp.async) staging path of the tiled kernels. */
+int         arf_debug_set(int key, int value);
 
 /* ---------------------------------------------------------------- correlation ---------- */
 /* Output dims of the cost volume, same arithmetic as correlation_cuda.cc:25-34. */

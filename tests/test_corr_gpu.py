@@ -82,3 +82,21 @@ def test_linearity_at_full_size():
     f2s = torch.roll(f2, shifts=1, dims=3)
     cvs = compute_cost_volume(f1, f2s, 4)
     assert_close(cvs[:, 41, :, 8:-8], cv[:, 40, :, 8:-8], RTOL_VALUE)
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 24, 32), (1, 20, 17, 44), (2, 8, 40, 36)])
+def test_cp_async_staging_path_matches_tma_path(oracle, shape):
+    """W % 4 == 0 shapes run the TMA producer; the debug hook forces the cp.async producer that serves
+    every other width.  Both must give the same cost volume."""
+    from arflow_b200 import _lib
+    from arflow_b200.correlation import compute_cost_volume
+    gen = torch.Generator().manual_seed(5)
+    f1, f2 = torch.randn(shape, generator=gen).cuda(), torch.randn(shape, generator=gen).cuda()
+    a = compute_cost_volume(f1, f2, 4)
+    _lib.call("arf_debug_set", 0, 1)
+    try:
+        b = compute_cost_volume(f1, f2, 4)
+    finally:
+        _lib.call("arf_debug_set", 0, 0)
+    assert torch.equal(a, b)
+    assert_close(a, oracle.corr_fwd_c(f1.cpu(), f2.cpu()), RTOL_VALUE)
