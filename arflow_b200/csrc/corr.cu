@@ -258,9 +258,13 @@ constexpr int kNFBar = kBC / kBCg;                     // one "F arrived" barrie
 
 template <bool kSecond>
 struct BwdSmem {
+    // The second gradient reads gO at (y-dy, x-dx): its slab carries the 4-px halo in both directions.
+    // (A tiled TMA load needs a 16-byte aligned innermost coordinate — measured: x0-3 raises "illegal
+    // instruction" — so the horizontal shift is applied when reading, not when loading.)
     static constexpr int kSlabRows = kSecond ? kBHH : kBTH;
+    static constexpr int kSlabW = kSecond ? kHW : kTW;
     float F[kBC][kBHH][kHW];                    // 122 880 B : halo tile of the other feature map
-    float slab[kBStages][kD][kSlabRows][kTW];   // 3 x 18 432 B (first) / 3 x 27 648 B (second)
+    float slab[kBStages][kD][kSlabRows][kSlabW];  // 3 x 18 432 B (first) / 3 x 34 560 B (second)
     uint64_t f_full[kNFBar], f_empty, s_full[kBStages], s_empty[kBStages];
 };
 
@@ -271,6 +275,7 @@ corr_bwd_md4(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ C
              int B, int C, int H, int W, int tiles_x, int tiles_y, int nsuper, float inv_c) {
     using Smem = BwdSmem<kSecond>;
     constexpr int kSlabRows = Smem::kSlabRows;
+    constexpr int kSlabW = Smem::kSlabW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
@@ -326,21 +331,21 @@ corr_bwd_md4(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ C
             for (int dx = 0; dx < kD; ++dx, ++it) {
                 const int s = it % kBStages;
                 arf::mbar_wait(&sm.s_empty[s], ((it / kBStages) & 1) ^ 1);
-                // first: rows y0.., columns x0..            second: rows y0-4.., columns shifted by -(dx-4)
-                const int sx = kSecond ? x0 - (dx - kMD) : x0;
+                // first: the tile itself; second: the tile with its 4-px halo
+                const int sx = kSecond ? x0 - kMD : x0;
                 const int sy = kSecond ? y0 - kMD : y0;
                 if (kTma) {
                     if (lane == 0) {
-                        arf::mbar_arrive_expect_tx(&sm.s_full[s], kD * kSlabRows * kTW * 4);
+                        arf::mbar_arrive_expect_tx(&sm.s_full[s], kD * kSlabRows * kSlabW * 4);
                         arf::tma_load_5d(&sm.slab[s][0][0][0], &mapG, &sm.s_full[s], sx, sy, dx, 0, b);
                     }
                 } else {
                     const float* gb = gout + (size_t)b * kD * kD * plane;
-                    for (int e = lane; e < kD * kSlabRows * kTW; e += 32) {
-                        int rr = (e / kTW) % kSlabRows, dy = e / (kTW * kSlabRows);
-                        int gx = sx + lane, gy = sy + rr;
+                    for (int e = lane; e < kD * kSlabRows * kSlabW; e += 32) {
+                        int xx = e % kSlabW, rr = (e / kSlabW) % kSlabRows, dy = e / (kSlabW * kSlabRows);
+                        int gx = sx + xx, gy = sy + rr;
                         bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-                        arf::cp_async_4_zfill(&sm.slab[s][dy][rr][lane],
+                        arf::cp_async_4_zfill(&sm.slab[s][dy][rr][xx],
                                               ok ? gb + (size_t)(dy * kD + dx) * plane + (size_t)gy * W + gx : gb, ok);
                     }
                     arf::cp_async_mbar_arrive_noinc(&sm.s_full[s]);
@@ -372,15 +377,15 @@ corr_bwd_md4(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ C
         for (int dx = 0; dx < kD; ++dx, ++it) {
             const int s = it % kBStages;
             arf::mbar_wait(&sm.s_full[s], (it / kBStages) & 1);
+            const int col = kSecond ? lane + 2 * kMD - dx : lane + dx;   // column in the halo frame
             float g[kTH][kD];
 #pragma unroll
             for (int r = 0; r < kTH; ++r)
 #pragma unroll
                 for (int d = 0; d < kD; ++d)
-                    g[r][d] = kSecond ? sm.slab[s][d][r0 + r + 2 * kMD - d][lane] : sm.slab[s][d][r0 + r][lane];
+                    g[r][d] = kSecond ? sm.slab[s][d][r0 + r + 2 * kMD - d][col] : sm.slab[s][d][r0 + r][lane];
             __syncwarp();
             if (lane == 0) arf::mbar_arrive(&sm.s_empty[s]);
-            const int col = kSecond ? lane + 2 * kMD - dx : lane + dx;
 #pragma unroll
             for (int c = 0; c < kBCg; ++c) {
                 float bb[kHH];
@@ -419,10 +424,11 @@ int launch_bwd_md4(const float* Fsrc, const float* gout, float* gin, int B, int 
     const long long nitems = (long long)tiles_x * tiles_y * B * nsuper;
     const int grid = (int)(nitems < ARF_NUM_SMS ? nitems : ARF_NUM_SMS);
     constexpr int rows = BwdSmem<kSecond>::kSlabRows;
+    constexpr int cols = BwdSmem<kSecond>::kSlabW;
     CUtensorMap mF, mG;
     bool tma = want_tma && arf::tma_ok_nchw(Fsrc, W) && arf::tma_ok_nchw(gout, W) &&
                arf::make_map_nchw(&mF, Fsrc, B, C, H, W, kHW, kBHH, kBCg) &&
-               arf::make_map_costvol(&mG, gout, B, kD, H, W, kTW, rows);
+               arf::make_map_costvol(&mG, gout, B, kD, H, W, cols, rows);
     const float inv_c = 1.0f / (float)C;
     const size_t smem = sizeof(BwdSmem<kSecond>);
     if (tma) {
