@@ -25,6 +25,18 @@ PROTOTYPES = {
     "arf_corr_bwd": [_P, _P, _P, _P, _P] + [c_int] * 9 + [_P],
     "arf_warp_fwd": [_P, _P, _P] + [c_int] * 6 + [c_float, c_float] + [c_int] * 4 + [_P],
     "arf_warp_bwd": [_P, _P, _P, _P, _P] + [c_int] * 6 + [c_float, c_float] + [c_int] * 4 + [_P],
+    "arf_inside_mask": [_P, _P] + [c_int] * 5 + [_P],
+    "arf_range_map": [_P, _P] + [c_int] * 4 + [_P],
+    "arf_count_to_mask": [_P, _P, ctypes.c_longlong, c_int, c_float, _P],
+    "arf_occ_bidir": [_P, _P, _P] + [c_int] * 3 + [c_float, c_float, _P],
+    "arf_resize_bilinear_fwd": [_P, _P, ctypes.c_longlong] + [c_int] * 4 + [c_float] * 3 + [_P],
+    "arf_resize_bilinear_bwd": [_P, _P, ctypes.c_longlong] + [c_int] * 4 + [c_float] * 3 + [_P],
+    "arf_census_num_partials": [c_int] * 3,
+    "arf_census_fwd": [_P] * 6 + [c_int] * 4 + [c_float] * 3 + [_P],
+    "arf_census_bwd": [_P] * 9 + [c_int] * 4 + [c_float] * 3 + [_P],
+    "arf_smooth_num_partials": [c_int] * 3,
+    "arf_smooth_fwd": [_P] * 4 + [c_int] * 8 + [c_float] * 3 + [_P],
+    "arf_smooth_bwd": [_P] * 4 + [c_int] * 8 + [c_float] * 3 + [_P],
 }
 _RESTYPES = {"arf_error_string": ctypes.c_char_p}
 

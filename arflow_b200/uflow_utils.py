@@ -2,7 +2,7 @@
 import torch
 
 from . import _lib
-from .warp_utils import FIELD_COORDS, _WarpFunction
+from .warp_utils import FIELD_COORDS, _WarpFunction  # noqa: F401
 
 
 def flow_to_warp(flow):
@@ -20,3 +20,217 @@ def resample(source, coords):
     align_corners=True; coordinates go through the same 2*c/max(W-1,1)-1 normalisation round trip."""
     _, _, H, W = source.shape
     return _WarpFunction.apply(source, coords, max(W - 1, 1), max(H - 1, 1), FIELD_COORDS, 0, 0, True)
+
+
+# --------------------------------------------------------------------------- masks ---------
+def _new_like(t, shape):
+    return torch.empty(shape, dtype=t.dtype, device=t.device)
+
+
+def mask_invalid(coords):
+    """uflow_utils.py:35-50 — 1 where the coordinate lies inside [0,W-1]x[0,H-1]."""
+    coords = coords.detach().contiguous()
+    B, _, H, W = coords.shape
+    with torch.cuda.device_of(coords):
+        mask = _new_like(coords, (B, 1, H, W))
+        _lib.call("arf_inside_mask", _lib.dev_ptr(coords, "coords"), _lib.dev_ptr(mask), B, H, W, FIELD_COORDS, 0,
+                  _lib.stream_ptr())
+    return mask
+
+
+def compute_range_map(flow):
+    """uflow_utils.py:80-160 — how often each pixel is hit by the forward splat of `flow`
+    (bilinear weights, targets outside the image dropped).  Every call site detaches the result
+    (uflow_loss.py:43,48; uflow_elbo_loss.py:50,57), so it is returned without a graph."""
+    assert flow.dim() == 4
+    flow = flow.detach().contiguous()
+    B, _, H, W = flow.shape
+    with torch.cuda.device_of(flow):
+        count = _new_like(flow, (B, 1, H, W))
+        _lib.call("arf_range_map", _lib.dev_ptr(flow, "flow"), _lib.dev_ptr(count), B, H, W, 0, _lib.stream_ptr())
+    return count
+
+
+def clamp01(count, mode=0, th=0.0):
+    """clamp(count, 0, 1) (mode 0), clamp < th (mode 1), 1 - clamp (mode 2) in one pass."""
+    count = count.contiguous()
+    with torch.cuda.device_of(count):
+        out = torch.empty_like(count)
+        _lib.call("arf_count_to_mask", _lib.dev_ptr(count), _lib.dev_ptr(out), count.numel(), mode, float(th),
+                  _lib.stream_ptr())
+    return out
+
+
+# --------------------------------------------------------------------------- resize --------
+class _ResizeFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, Ho, Wo, rh, rw, mul):
+        img = img.contiguous()
+        B, C, Hi, Wi = img.shape
+        args = (B * C, Hi, Wi, Ho, Wo, float(rh), float(rw), float(mul))
+        with torch.cuda.device_of(img):
+            out = _new_like(img, (B, C, Ho, Wo))
+            _lib.call("arf_resize_bilinear_fwd", _lib.dev_ptr(img, "img"), _lib.dev_ptr(out), *args, _lib.stream_ptr())
+        ctx.args = args
+        ctx.in_shape = img.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        gout = gout.contiguous()
+        with torch.cuda.device_of(gout):
+            gin = _new_like(gout, ctx.in_shape)
+            _lib.call("arf_resize_bilinear_bwd", _lib.dev_ptr(gout, "grad"), _lib.dev_ptr(gin), *ctx.args,
+                      _lib.stream_ptr())
+        return gin, None, None, None, None, None
+
+
+def _interpolate(img, scale_factor, mul):
+    # F.interpolate(scale_factor=s): output size floor(in*s); source step exactly 1/s
+    import math
+    _, _, H, W = img.shape
+    Ho, Wo = int(math.floor(H * scale_factor)), int(math.floor(W * scale_factor))
+    return _ResizeFunction.apply(img, Ho, Wo, 1.0 / scale_factor, 1.0 / scale_factor, mul)
+
+
+def upsample(img, is_flow, scale_factor=2.0):
+    """uflow_utils.py:163-182 — bilinear, align_corners=False; flow values scaled with the size."""
+    return _interpolate(img, scale_factor, scale_factor if is_flow else 1.0)
+
+
+def downsample(img, is_flow, scale_factor=2.0):
+    """uflow_utils.py:185-204."""
+    return _interpolate(img, 1 / scale_factor, 1 / scale_factor if is_flow else 1.0)
+
+
+# --------------------------------------------------------------------------- small helpers -
+def image_grads(image_batch, stride=1):
+    """uflow_utils.py:207-210 (slicing only)."""
+    image_batch_x = image_batch[:, :, :, stride:] - image_batch[:, :, :, :-stride]
+    image_batch_y = image_batch[:, :, stride:] - image_batch[:, :, :-stride]
+    return image_batch_x, image_batch_y
+
+
+def abs_robust_loss(diff, eps=0.01, q=0.4):
+    """uflow_utils.py:213-214."""
+    return torch.pow((torch.abs(diff) + eps), q)
+
+
+def robust_l1(x):
+    """uflow_utils.py:337-338."""
+    return (x + 0.001 ** 2) ** 0.5
+
+
+def rgb_to_grayscale(image):
+    """uflow_utils.py:227-231."""
+    grayscale = image[:, 0, :, :] * 0.2989 + image[:, 1, :, :] * 0.5870 + image[:, 2, :, :] * 0.1140
+    return grayscale.unsqueeze(1)
+
+
+def zero_mask_border(mask, patch_size):
+    """uflow_utils.py:234-238."""
+    p = patch_size // 2
+    return torch.nn.functional.pad(mask[:, :, p:-p, p:-p], [p] * 4)
+
+
+# --------------------------------------------------------------------------- census --------
+class _CensusHammingFunction(torch.autograd.Function):
+    """soft_hamming(census_transform(a), census_transform(b)) in one pass (uflow_utils.py:241-279)."""
+
+    @staticmethod
+    def forward(ctx, im_a, im_b, patch, scale):
+        im_a, im_b = im_a.contiguous(), im_b.contiguous()
+        if im_a.shape != im_b.shape or im_a.dim() != 4 or im_a.shape[1] != 3:
+            raise ValueError("census: expected two (B,3,H,W) images of equal shape")
+        B, _, H, W = im_a.shape
+        with torch.cuda.device_of(im_a):
+            ham = _new_like(im_a, (B, 1, H, W))
+            _lib.call("arf_census_fwd", _lib.dev_ptr(im_a, "image_a"), _lib.dev_ptr(im_b, "image_b"), None,
+                      _lib.dev_ptr(ham), None, None, B, H, W, patch, float(scale), 0.01, 0.4, _lib.stream_ptr())
+        ctx.save_for_backward(im_a, im_b)
+        ctx.cfg = (patch, float(scale))
+        return ham
+
+    @staticmethod
+    def backward(ctx, gham):
+        im_a, im_b = ctx.saved_tensors
+        patch, scale = ctx.cfg
+        B, _, H, W = im_a.shape
+        gham = gham.contiguous()
+        with torch.cuda.device_of(im_a):
+            ga = torch.empty_like(im_a) if ctx.needs_input_grad[0] else None
+            gb = torch.empty_like(im_b) if ctx.needs_input_grad[1] else None
+            _lib.call("arf_census_bwd", _lib.dev_ptr(im_a), _lib.dev_ptr(im_b), _lib.dev_ptr(gham, "grad"), None, None,
+                      None, None, _lib.dev_ptr(ga, allow_none=True), _lib.dev_ptr(gb, allow_none=True),
+                      B, H, W, patch, scale, 0.01, 0.4, _lib.stream_ptr())
+        return ga, gb, None, None
+
+
+class _CensusLossFunction(torch.autograd.Function):
+    """census_loss (uflow_utils.py:282-293) fused: transform, soft Hamming, robust penalty, border-zeroed
+    mask and the batch-global masked mean, one pass forward and one pass backward."""
+
+    @staticmethod
+    def forward(ctx, im_a, im_b, mask, patch, eps, q):
+        im_a, im_b = im_a.contiguous(), im_b.contiguous()
+        if im_a.shape != im_b.shape or im_a.dim() != 4 or im_a.shape[1] != 3:
+            raise ValueError("census_loss: expected two (B,3,H,W) images of equal shape")
+        B, _, H, W = im_a.shape
+        mask = mask.detach().contiguous()
+        if mask.shape != (B, 1, H, W):
+            raise ValueError("census_loss: mask must be (B,1,H,W)")
+        lib = _lib.load()
+        with torch.cuda.device_of(im_a):
+            ham = _new_like(im_a, (B, 1, H, W))
+            partials = _new_like(im_a, (2 * lib.arf_census_num_partials(B, H, W),))
+            sums = _new_like(im_a, (3,))
+            _lib.call("arf_census_fwd", _lib.dev_ptr(im_a, "image_a"), _lib.dev_ptr(im_b, "image_b"),
+                      _lib.dev_ptr(mask, "mask"), _lib.dev_ptr(ham), _lib.dev_ptr(partials), _lib.dev_ptr(sums),
+                      B, H, W, patch, 1.0, float(eps), float(q), _lib.stream_ptr())
+        ctx.save_for_backward(im_a, im_b, mask, ham, sums)
+        ctx.cfg = (patch, float(eps), float(q))
+        return sums[2]
+
+    @staticmethod
+    def backward(ctx, gloss):
+        im_a, im_b, mask, ham, sums = ctx.saved_tensors
+        patch, eps, q = ctx.cfg
+        B, _, H, W = im_a.shape
+        gloss = gloss.reshape(1).contiguous()
+        with torch.cuda.device_of(im_a):
+            ga = torch.empty_like(im_a) if ctx.needs_input_grad[0] else None
+            gb = torch.empty_like(im_b) if ctx.needs_input_grad[1] else None
+            _lib.call("arf_census_bwd", _lib.dev_ptr(im_a), _lib.dev_ptr(im_b), None, _lib.dev_ptr(ham),
+                      _lib.dev_ptr(mask), _lib.dev_ptr(sums), _lib.dev_ptr(gloss, "grad"),
+                      _lib.dev_ptr(ga, allow_none=True), _lib.dev_ptr(gb, allow_none=True),
+                      B, H, W, patch, 1.0, eps, q, _lib.stream_ptr())
+        return ga, gb, None, None, None, None
+
+
+def census_transform(image, patch_size):
+    """uflow_utils.py:241-261 — the explicit patch*patch-channel transform (compatibility helper; the loss
+    functions below never materialise it)."""
+    intensities = rgb_to_grayscale(image) * 255
+    p = patch_size // 2
+    neighbors = torch.nn.functional.unfold(intensities, patch_size, padding=p)
+    neighbors = neighbors.view(image.shape[0], patch_size * patch_size, image.shape[2], image.shape[3])
+    diff = neighbors - intensities
+    return diff / torch.sqrt(.81 + torch.square(diff))
+
+
+def soft_hamming(a, b, thresh=.1):
+    """uflow_utils.py:264-279."""
+    sq_dist = torch.square(a - b)
+    return torch.sum(sq_dist / (thresh + sq_dist), 1, keepdim=True)
+
+
+def census_loss(image_a, image_b, mask, patch_size=7):
+    """uflow_utils.py:282-293."""
+    return _CensusLossFunction.apply(image_a, image_b, mask, patch_size, 0.01, 0.4)
+
+
+def census_loss_no_penalty(image_a, image_b, mask, patch_size=7):
+    """uflow_utils.py:296-306 — per-pixel soft Hamming distance and normalised weight map."""
+    hamming = _CensusHammingFunction.apply(image_a, image_b, patch_size, 1.0)
+    padded_mask = zero_mask_border(mask, patch_size)
+    return hamming, padded_mask / (torch.sum(padded_mask.detach()) + 1e-6)

@@ -63,3 +63,86 @@ def flow_warp(x, flow, pad='zeros', mode='bilinear', align_corners=True):
     pad_mode, interp = _modes(pad, mode)
     _, _, H, W = flow.shape
     return _WarpFunction.apply(x, flow, W - 1, H - 1, FIELD_FLOW, interp, pad_mode, bool(align_corners))
+
+
+# --------------------------------------------------------------------------- grids, masks --
+def mesh_grid(B, H, W):
+    """warp_utils.py:7-13 (integer pixel grid, B x 2 x H x W, CPU like the reference)."""
+    x_base = torch.arange(0, W).repeat(B, H, 1)
+    y_base = torch.arange(0, H).repeat(B, W, 1).transpose(1, 2)
+    return torch.stack([x_base, y_base], 1)
+
+
+def norm_grid(v_grid):
+    """warp_utils.py:16-23."""
+    _, _, H, W = v_grid.size()
+    v_grid_norm = torch.zeros_like(v_grid)
+    v_grid_norm[:, 0, :, :] = 2.0 * v_grid[:, 0, :, :] / (W - 1) - 1.0
+    v_grid_norm[:, 1, :, :] = 2.0 * v_grid[:, 1, :, :] / (H - 1) - 1.0
+    return v_grid_norm.permute(0, 2, 3, 1)
+
+
+def _splat(field, kind):
+    field = field.detach().contiguous()
+    B, _, H, W = field.shape
+    with torch.cuda.device_of(field):
+        count = torch.empty((B, 1, H, W), dtype=field.dtype, device=field.device)
+        _lib.call("arf_range_map", _lib.dev_ptr(field, "flow"), _lib.dev_ptr(count), B, H, W, kind, _lib.stream_ptr())
+    return count
+
+
+def get_corresponding_map(data):
+    """warp_utils.py:26-80 — forward splat of unnormalised coordinates (B,2,H,W) -> (B,1,H,W)."""
+    return _splat(data, FIELD_COORDS)
+
+
+def compute_range_map(flow):
+    """warp_utils.py:158-239 (identical to uflow_utils.compute_range_map)."""
+    assert flow.dim() == 4
+    return _splat(flow, FIELD_FLOW)
+
+
+def _count_to_mask(count, mode, th=0.0):
+    with torch.cuda.device_of(count):
+        out = torch.empty_like(count)
+        _lib.call("arf_count_to_mask", _lib.dev_ptr(count), _lib.dev_ptr(out), count.numel(), mode, float(th),
+                  _lib.stream_ptr())
+    return out
+
+
+def get_occu_mask_backward(flow21, th=0.2):
+    """warp_utils.py:103-116 — 1 (or close to 1) at occluded pixels."""
+    corr_map = _splat(flow21, FIELD_FLOW)  # get_corresponding_map(base_grid + flow21)
+    return _count_to_mask(corr_map, 1, th) if th > 0 else _count_to_mask(corr_map, 2)
+
+
+def get_occu_mask_bidirection(flow12, flow21, scale=0.01, bias=0.5):
+    """warp_utils.py:93-100 — forward-backward consistency check."""
+    flow21_warped = flow_warp(flow21, flow12, pad='zeros').detach()
+    flow12 = flow12.detach().contiguous()
+    B, _, H, W = flow12.shape
+    with torch.cuda.device_of(flow12):
+        occ = torch.empty((B, 1, H, W), dtype=flow12.dtype, device=flow12.device)
+        _lib.call("arf_occ_bidir", _lib.dev_ptr(flow12, "flow12"), _lib.dev_ptr(flow21_warped), _lib.dev_ptr(occ),
+                  B, H, W, float(scale), float(bias), _lib.stream_ptr())
+    return occ
+
+
+def border_mask(flow):
+    """warp_utils.py:119-134 — 1 where the correspondence lies strictly inside the image."""
+    flow = flow.detach().contiguous()
+    B, _, H, W = flow.shape
+    with torch.cuda.device_of(flow):
+        mask = torch.empty((B, 1, H, W), dtype=flow.dtype, device=flow.device)
+        _lib.call("arf_inside_mask", _lib.dev_ptr(flow, "flow"), _lib.dev_ptr(mask), B, H, W, FIELD_FLOW, 1,
+                  _lib.stream_ptr())
+    return mask
+
+
+def flow_to_warp(flow):
+    """warp_utils.py:138-155 — the NHWC, (y, x)-ordered variant kept by this module."""
+    flow = flow.permute(0, 2, 3, 1).flip(-1)
+    _, height, width, _ = flow.size()
+    i_grid, j_grid = torch.meshgrid(torch.arange(height, device=flow.device, dtype=flow.dtype),
+                                    torch.arange(width, device=flow.device, dtype=flow.dtype), indexing='ij')
+    return torch.stack([i_grid, j_grid], dim=2) + flow

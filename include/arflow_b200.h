@@ -96,6 +96,65 @@ int arf_warp_bwd(const float* x, const float* field, const float* gy, float* gx,
                  float nW1, float nH1, int field_kind, int interp, int pad_mode, int align_corners,
                  void* stream);
 
+/* ---------------------------------------------------------------- masks / range map ---- */
+/* strict=0: mask_invalid (uflow_utils.py:35-50), 1[0<=x<=W-1 && 0<=y<=H-1];
+ * strict=1: border_mask (warp_utils.py:119-134), 1[0<x<W-1 && 0<y<H-1].  field (B,2,H,W) -> mask (B,1,H,W). */
+int arf_inside_mask(const float* field, float* mask, int B, int H, int W, int field_kind, int strict, void* stream);
+
+/* compute_range_map (uflow_utils.py:80-160, warp_utils.py:158-239; field_kind FLOW) and
+ * get_corresponding_map (warp_utils.py:26-80; field_kind COORDS): bilinear forward splat count.
+ * count (B,1,H,W) is zero-filled here. */
+int arf_range_map(const float* field, float* count, int B, int H, int W, int field_kind, void* stream);
+
+/* mode 0: clamp(c,0,1)   1: clamp(c,0,1) < th   2: 1 - clamp(c,0,1)     (uflow_loss.py:41, warp_utils.py:111-116) */
+int arf_count_to_mask(const float* count, float* out, long long n, int mode, float th, void* stream);
+
+/* get_occu_mask_bidirection tail (warp_utils.py:93-100): out = |f12+f21w|^2 > scale*(|f12|^2+|f21w|^2)+bias */
+int arf_occ_bidir(const float* flow12, const float* flow21_warped, float* out, int B, int H, int W,
+                  float scale, float bias, void* stream);
+
+/* ---------------------------------------------------------------- bilinear resize ------ */
+/* F.interpolate(mode='bilinear', align_corners=False) as used by upsample/downsample (uflow_utils.py:163-204):
+ * rh, rw = source step per destination pixel (= 1/scale_factor), out = mul * interp (mul scales flow values).
+ * in: (planes,Hi,Wi) -> out: (planes,Ho,Wo).  The backward is a deterministic gather. */
+int arf_resize_bilinear_fwd(const float* in, float* out, long long planes, int Hi, int Wi, int Ho, int Wo,
+                            float rh, float rw, float mul, void* stream);
+int arf_resize_bilinear_bwd(const float* gout, float* gin, long long planes, int Hi, int Wi, int Ho, int Wo,
+                            float rh, float rw, float mul, void* stream);
+
+/* ---------------------------------------------------------------- census / ternary ----- */
+/* Number of per-CTA partial sums (2 floats each) the fused reduction needs for a (B,3,H,W) image pair. */
+int arf_census_num_partials(int B, int H, int W);
+
+/* hamming[b,0,y,x] = scale * sum_k sq_k/(0.1+sq_k), sq_k = (t_a,k - t_b,k)^2, t = d/sqrt(0.81+d^2),
+ * d = gray255(neighbour k) - gray255(centre), zero outside the image (census_transform + soft_hamming,
+ * uflow_utils.py:241-279; TernaryLoss, loss_blocks.py:12-62; scale = 1 for the sum, 1/patch^2 for the mean).
+ * If sums != NULL also: sums[0] = sum((|h|+eps)^q * pm), sums[1] = sum(pm), sums[2] = sums[0]/(sums[1]+1e-6)
+ * with pm = mask with a patch/2 border zeroed (mask NULL = ones) — census_loss, uflow_utils.py:282-293.
+ * im_a, im_b: (B,3,H,W); mask, hamming: (B,1,H,W); partials: 2*arf_census_num_partials floats. patch in {3,5,7}. */
+int arf_census_fwd(const float* im_a, const float* im_b, const float* mask, float* hamming,
+                   float* partials, float* sums, int B, int H, int W, int patch, float scale,
+                   float eps, float q, void* stream);
+
+/* Gradients w.r.t. the RGB images (either may be NULL).  Upstream gradient: ghamming (B,1,H,W) if given,
+ * else the fused census_loss tail is differentiated from (hamming, mask, sums, gloss[0]). */
+int arf_census_bwd(const float* im_a, const float* im_b, const float* ghamming, const float* hamming,
+                   const float* mask, const float* sums, const float* gloss, float* g_a, float* g_b,
+                   int B, int H, int W, int patch, float scale, float eps, float q, void* stream);
+
+/* ---------------------------------------------------------------- smoothness ----------- */
+int arf_smooth_num_partials(int B, int H, int W);
+
+/* out[0] = final_scale * (mean_x(w_x*pen(d_x)) + mean_y(w_y*pen(d_y))), see csrc/smooth.cu for the
+ * parameter table (uflow_loss.py:58-102, loss_blocks.py:93-124).  img: (B,Ci,H,W), flow: (B,2,H,W).
+ * penalty 0: sqrt(d^2+eps2), 1: |d|.  partials: 2*arf_smooth_num_partials floats. */
+int arf_smooth_fwd(const float* img, const float* flow, float* out, float* partials, int B, int Ci, int H, int W,
+                   int order, int wstride, int woff, int penalty, float edge, float eps2, float final_scale,
+                   void* stream);
+int arf_smooth_bwd(const float* img, const float* flow, const float* gloss, float* gflow, int B, int Ci, int H, int W,
+                   int order, int wstride, int woff, int penalty, float edge, float eps2, float final_scale,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

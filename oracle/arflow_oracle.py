@@ -156,3 +156,193 @@ def flow_to_warp(flow):
     jj = torch.arange(W, dtype=flow.dtype).view(1, 1, 1, W).expand(B, 1, H, W)
     ii = torch.arange(H, dtype=flow.dtype).view(1, 1, H, 1).expand(B, 1, H, W)
     return torch.cat([jj, ii], 1) + flow
+
+
+# --------------------------------------------------------------------------- masks ----------
+def mask_invalid(coords):
+    """uflow_utils.py:35-50."""
+    H, W = coords.shape[2:]
+    x, y = coords[:, 0:1], coords[:, 1:2]
+    return ((x >= 0) & (x <= W - 1) & (y >= 0) & (y <= H - 1)).to(coords.dtype)
+
+
+def border_mask(flow):
+    """warp_utils.py:119-134."""
+    H, W = flow.shape[2:]
+    c = flow_to_warp(flow)
+    x, y = c[:, 0:1], c[:, 1:2]
+    return ((x > 0) & (x < W - 1) & (y > 0) & (y < H - 1)).to(flow.dtype)
+
+
+def splat_count(coords):
+    """The scatter shared by compute_range_map (uflow_utils.py:80-160, warp_utils.py:158-239) and
+    get_corresponding_map (warp_utils.py:26-80): bilinear weights of every target added to its four
+    integer neighbours, neighbours outside the image dropped."""
+    B, _, H, W = coords.shape
+    x, y = coords[:, 0].reshape(B, -1), coords[:, 1].reshape(B, -1)
+    x0, y0 = torch.floor(x), torch.floor(y)
+    fx, fy = x - x0, y - y0
+    out = torch.zeros(B, H * W, dtype=coords.dtype)
+    for dy, wy in ((0, 1 - fy), (1, fy)):
+        for dx, wx in ((0, 1 - fx), (1, fx)):
+            xi, yi = (x0 + dx).long(), (y0 + dy).long()
+            ok = (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H)
+            lin = yi.clamp(0, H - 1) * W + xi.clamp(0, W - 1)
+            out.scatter_add_(1, lin, wy * wx * ok.to(coords.dtype))
+    return out.view(B, 1, H, W)
+
+
+def range_map(flow):
+    return splat_count(flow_to_warp(flow))
+
+
+def occu_mask_backward(flow21, th=0.2):
+    """warp_utils.py:103-116."""
+    c = range_map(flow21).clamp(0, 1)
+    return (c < th).to(flow21.dtype) if th > 0 else 1 - c
+
+
+def occu_mask_bidirection(flow12, flow21, scale=0.01, bias=0.5):
+    """warp_utils.py:93-100."""
+    w = warp(flow21, flow12, kind="flow")
+    mag = (flow12 ** 2).sum(1, keepdim=True) + (w ** 2).sum(1, keepdim=True)
+    return (((flow12 + w) ** 2).sum(1, keepdim=True) > scale * mag + bias).to(flow12.dtype)
+
+
+# --------------------------------------------------------------------------- resize ---------
+def _lin_taps(n_out, n_in, step, dtype):
+    # ATen area_pixel_compute_source_index, align_corners=False, clamp below at 0
+    s = (step * (torch.arange(n_out, dtype=dtype) + 0.5) - 0.5).clamp(min=0)
+    i0 = s.floor().long().clamp(max=n_in - 1)
+    i1 = (i0 + 1).clamp(max=n_in - 1)
+    l1 = s - i0.to(dtype)
+    return i0, i1, 1 - l1, l1
+
+
+def resize_bilinear(img, scale_factor, is_flow):
+    """upsample / downsample of uflow_utils.py:163-204 (pass scale_factor < 1 to downsample)."""
+    B, C, H, W = img.shape
+    Ho, Wo = int(math.floor(H * scale_factor)), int(math.floor(W * scale_factor))
+    y0, y1, hy0, hy1 = _lin_taps(Ho, H, 1.0 / scale_factor, img.dtype)
+    x0, x1, wx0, wx1 = _lin_taps(Wo, W, 1.0 / scale_factor, img.dtype)
+    top = img[:, :, y0][:, :, :, x0] * wx0 + img[:, :, y0][:, :, :, x1] * wx1
+    bot = img[:, :, y1][:, :, :, x0] * wx0 + img[:, :, y1][:, :, :, x1] * wx1
+    out = top * hy0.view(-1, 1) + bot * hy1.view(-1, 1)
+    return out * scale_factor if is_flow else out
+
+
+# --------------------------------------------------------------------------- census ---------
+def _gray255(im):
+    return ((im[:, 0] * 0.2989 + im[:, 1] * 0.5870 + im[:, 2] * 0.1140) * 255).unsqueeze(1)
+
+
+def census_hamming(im_a, im_b, patch=7, mean=False):
+    """soft_hamming(census_transform(a), census_transform(b)) (uflow_utils.py:241-279), offset by offset
+    instead of through a patch*patch-channel identity convolution.  mean=True: TernaryLoss ARFlow variant."""
+    r = patch // 2
+    ga, gb = _gray255(im_a), _gray255(im_b)
+    pa, pb = F.pad(ga, [r] * 4), F.pad(gb, [r] * 4)
+    H, W = ga.shape[2:]
+    h = torch.zeros_like(ga)
+    for dy in range(patch):
+        for dx in range(patch):
+            da = pa[:, :, dy:dy + H, dx:dx + W] - ga
+            db = pb[:, :, dy:dy + H, dx:dx + W] - gb
+            ta = da / torch.sqrt(0.81 + da * da)
+            tb = db / torch.sqrt(0.81 + db * db)
+            sq = (ta - tb) ** 2
+            h = h + sq / (0.1 + sq)
+    return h / (patch * patch) if mean else h
+
+
+def zero_border(mask, r):
+    out = torch.zeros_like(mask)
+    out[:, :, r:-r, r:-r] = mask[:, :, r:-r, r:-r]
+    return out
+
+
+def census_loss(im_a, im_b, mask, patch=7):
+    """uflow_utils.py:282-293."""
+    h = census_hamming(im_a, im_b, patch)
+    pm = zero_border(mask, patch // 2)
+    return ((h.abs() + 0.01) ** 0.4 * pm).sum() / (pm.detach().sum() + 1e-6)
+
+
+def census_loss_no_penalty(im_a, im_b, mask, patch=7):
+    """uflow_utils.py:296-306."""
+    pm = zero_border(mask, patch // 2)
+    return census_hamming(im_a, im_b, patch), pm / (pm.detach().sum() + 1e-6)
+
+
+def ternary_loss(im, im_warp, max_distance=1, sum_dist=False):
+    """loss_blocks.py:12-62 -> (dist, mask)."""
+    patch = 2 * max_distance + 1
+    dist = census_hamming(im, im_warp, patch, mean=not sum_dist)
+    mask = zero_border(torch.ones_like(dist), max_distance)
+    return dist, mask
+
+
+# --------------------------------------------------------------------------- smoothness -----
+def _diff(t, dim, stride=1):
+    n = t.shape[dim]
+    return t.narrow(dim, stride, n - stride) - t.narrow(dim, 0, n - stride)
+
+
+def smooth_uflow(im_2, flow_2, edge_constant, w_smooth, order=1):
+    """One direction of the smoothness block of UFlowLoss.forward (uflow_loss.py:62-102); im_2 is the
+    quarter-resolution image."""
+    total = 0
+    for dim in (3, 2):
+        g = _diff(im_2.detach(), dim, stride=order)
+        w = torch.exp(-(edge_constant * g).abs().mean(1, keepdim=True))
+        d = _diff(flow_2, dim)
+        if order == 2:
+            d = _diff(d, dim)
+        total = total + (w * (d * d + 0.001 ** 2) ** 0.5).mean()
+    return w_smooth * total / 2.0
+
+
+def smooth_grad_1st(flo, image, alpha, penalty="abs"):
+    """loss_blocks.py:93-109."""
+    total = 0
+    for dim in (3, 2):
+        w = torch.exp(-_diff(image, dim).abs().mean(1, keepdim=True) * alpha)
+        d = _diff(flo, dim)
+        p = d.abs() if penalty == "abs" else torch.sqrt(d * d + 0.001 ** 2)
+        total = total + (w * p / 2.0).mean() / 2.0
+    return total
+
+
+def smooth_grad_2nd(flo, image, alpha):
+    """loss_blocks.py:112-124."""
+    total = 0
+    for dim in (3, 2):
+        w = torch.exp(-_diff(image, dim).abs().mean(1, keepdim=True) * alpha)
+        d2 = _diff(_diff(flo, dim), dim)
+        n = w.shape[dim]
+        total = total + (w.narrow(dim, 1, n - 1) * d2.abs()).mean() / 2.0
+    return total
+
+
+def uflow_loss(output, target, w_census=1.0, w_smooth=4.0, edge_constant=150.0, with_bk=True, smooth_order=1):
+    """UFlowLoss.forward (uflow_loss.py:13-109) -> (total, loss_warp, loss_smooth, mean|flow|, mask1)."""
+    f12_0, f21_0 = output[0][:, 0:2], output[0][:, 2:4]
+    f12_2, f21_2 = output[2][:, 0:2], output[2][:, 2:4]
+    im1, im2 = target[:, :3], target[:, 3:]
+
+    def direction(im_a, im_b, f_ab_0, f_ba_2):
+        w0 = flow_to_warp(f_ab_0)
+        recons = warp(im_b.detach(), w0, kind="coords")
+        occ = resize_bilinear(range_map(f_ba_2).clamp(0, 1), 4.0, False)
+        mask = (occ * mask_invalid(w0)).detach()
+        return census_loss(im_a, recons, mask), mask
+
+    l1, mask1 = direction(im1, im2, f12_0, f21_2)
+    loss_warp = w_census * l1
+    loss_smooth = smooth_uflow(resize_bilinear(im1, 0.25, False), f12_2, edge_constant, w_smooth, smooth_order)
+    if with_bk:
+        l2, _ = direction(im2, im1, f21_0, f12_2)
+        loss_warp = loss_warp + w_census * l2
+        loss_smooth = loss_smooth + smooth_uflow(resize_bilinear(im2, 0.25, False), f21_2, edge_constant, w_smooth,
+                                                 smooth_order)
+    return loss_warp + loss_smooth, loss_warp, loss_smooth, output[0].abs().mean(), mask1

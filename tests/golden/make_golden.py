@@ -98,6 +98,69 @@ def main():
     res = both(lambda a, f: uu.resample(a, uu.flow_to_warp(f)), x, flow, grads=(0, 1))
     save("resample", (x, flow), res)
 
+    # ---- masks / range map / occlusion ----
+    from utils import warp_utils as wu
+    flow = rnd(gen, 2, 2, 12, 16, scale=3.0)
+    flow_b = rnd(gen, 2, 2, 12, 16, scale=3.0)
+    res = {}
+    for k, v in both(lambda f: uu.mask_invalid(uu.flow_to_warp(f)), flow).items(): res["invalid_" + k] = v
+    for k, v in both(lambda f: uu.compute_range_map(f), flow).items(): res["range_" + k] = v
+    for k, v in both(lambda f: wu.compute_range_map(f), flow).items(): res["range_wu_" + k] = v
+    for k, v in both(lambda f: wu.get_corresponding_map(uu.flow_to_warp(f)), flow).items(): res["corrmap_" + k] = v
+    for k, v in both(lambda f: wu.get_occu_mask_backward(f, th=0.2), flow).items(): res["occ_bw_" + k] = v
+    for k, v in both(lambda f: wu.get_occu_mask_backward(f, th=0.0), flow).items(): res["occ_bw0_" + k] = v
+    for k, v in both(lambda f: wu.border_mask(f), flow).items(): res["border_" + k] = v
+    small, small_b = flow * 0.3, flow_b * 0.3
+    for k, v in both(lambda a, b: wu.get_occu_mask_bidirection(a, b), small, small_b).items(): res["occ_bi_" + k] = v
+    save("masks", (flow, flow_b), res)
+
+    # ---- resize ----
+    img = rnd(gen, 2, 3, 6, 10)
+    res = {}
+    for s in (2.0, 4.0):
+        for is_flow in (False, True):
+            for k, v in both(lambda a: uu.upsample(a, is_flow, scale_factor=s), img, grads=(0,)).items():
+                res["up%d_%d_%s" % (s, is_flow, k)] = v
+    big = rnd(gen, 2, 3, 16, 24)
+    for s in (2.0, 4.0):
+        for is_flow in (False, True):
+            for k, v in both(lambda a: uu.downsample(a, is_flow, scale_factor=s), big, grads=(0,)).items():
+                res["down%d_%d_%s" % (s, is_flow, k)] = v
+    save("resize", (img, big), res)
+
+    # ---- census / ternary ----
+    from losses import loss_blocks as lb
+    a, b = rnd(gen, 2, 3, 20, 24, uniform=True), rnd(gen, 2, 3, 20, 24, uniform=True)
+    mask = (rnd(gen, 2, 1, 20, 24, uniform=True) > 0.3).float() * rnd(gen, 2, 1, 20, 24, uniform=True)
+    res = {}
+    for k, v in both(lambda x, y, m: uu.census_loss(x, y, m), a, b, mask, grads=(0, 1)).items(): res["loss_" + k] = v
+    for k, v in both(lambda x, y, m: uu.census_loss_no_penalty(x, y, m), a, b, mask, grads=(0, 1)).items(): res["nopen_" + k] = v
+    for k, v in both(lambda x, y: lb.TernaryLoss(x, y, max_distance=1)[0], a, b, grads=(1,)).items(): res["tern1_" + k] = v
+    for k, v in both(lambda x, y: lb.TernaryLoss(x, y, max_distance=3, sum_dist=True)[0], a, b).items(): res["tern3s_" + k] = v
+    for k, v in both(lambda x, y: lb.TernaryLoss(x, y, max_distance=2)[1], a, b).items(): res["tern2mask_" + k] = v
+    save("census", (a, b, mask), res)
+
+    # ---- smoothness blocks of loss_blocks ----
+    flo, image = rnd(gen, 2, 2, 10, 14), rnd(gen, 2, 3, 10, 14, uniform=True)
+    res = {}
+    for k, v in both(lambda f, i: lb.smooth_grad_1st(f, i, 10.0), flo, image, grads=(0,)).items(): res["s1abs_" + k] = v
+    for k, v in both(lambda f, i: lb.smooth_grad_1st(f, i, 10.0, penalty="uflow"), flo, image, grads=(0,)).items(): res["s1uf_" + k] = v
+    for k, v in both(lambda f, i: lb.smooth_grad_2nd(f, i, 10.0), flo, image, grads=(0,)).items(): res["s2_" + k] = v
+    save("smooth_blocks", (flo, image), res)
+
+    # ---- UFlowLoss end to end (both smoothness orders) ----
+    from losses.uflow_loss import UFlowLoss
+    from easydict import EasyDict
+    H, W = 32, 40
+    out0 = rnd(gen, 2, 4, H, W, scale=2.0)
+    out1 = rnd(gen, 2, 4, H // 2, W // 2)
+    out2 = rnd(gen, 2, 4, H // 4, W // 4, scale=0.7)
+    target = rnd(gen, 2, 6, H, W, uniform=True)
+    for order in (1, 2):
+        cfg = EasyDict(edge_constant=150, w_smooth=4.0, w_census=1.0, with_bk=True, smooth_order=order)
+        res = both(lambda o0, o1, o2, t: UFlowLoss(cfg)([o0, o1, o2], t), out0, out1, out2, target, grads=(0, 2))
+        save("uflow_loss_order%d" % order, (out0, out1, out2, target), res)
+
 
 if __name__ == "__main__":
     torch.manual_seed(0)

@@ -1,0 +1,125 @@
+"""Parity of masks, resize, census, smoothness and the whole UFlowLoss with the golden fixtures (B200)."""
+import types
+
+import pytest
+import torch
+
+from conftest import RTOL_GRAD, RTOL_VALUE, assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _grads(fn, inputs, wrt):
+    ins = [i.cuda().clone().requires_grad_(k in wrt) for k, i in enumerate(inputs)]
+    out = fn(*ins)
+    outs = out if isinstance(out, (tuple, list)) else (out,)
+    g = torch.Generator().manual_seed(1234)
+    loss = 0
+    for o in outs:
+        w = torch.randn(o.shape, generator=g)
+        if o.requires_grad:
+            loss = loss + (o * w.cuda()).sum()
+    return outs, torch.autograd.grad(loss, [ins[k] for k in wrt])
+
+
+def test_masks_golden():
+    from arflow_b200 import uflow_utils as uu
+    from arflow_b200 import warp_utils as wu
+    g = load_golden("masks")
+    flow, flow_b = g["in0"].cuda(), g["in1"].cuda()
+    assert torch.equal(uu.mask_invalid(uu.flow_to_warp(flow)).cpu(), g["invalid_out0_f32"])
+    assert_close(uu.compute_range_map(flow), g["range_out0_f64"], RTOL_VALUE)
+    assert_close(wu.compute_range_map(flow), g["range_out0_f64"], RTOL_VALUE)
+    assert_close(wu.get_corresponding_map(uu.flow_to_warp(flow)), g["corrmap_out0_f64"], RTOL_VALUE)
+    assert torch.equal(wu.get_occu_mask_backward(flow, th=0.2).cpu(), g["occ_bw_out0_f32"])
+    assert_close(wu.get_occu_mask_backward(flow, th=0.0), g["occ_bw0_out0_f64"], RTOL_VALUE)
+    assert torch.equal(wu.border_mask(flow).cpu(), g["border_out0_f32"])
+    assert torch.equal(wu.get_occu_mask_bidirection(flow * 0.3, flow_b * 0.3).cpu(), g["occ_bi_out0_f32"])
+
+
+def test_resize_golden():
+    from arflow_b200 import uflow_utils as uu
+    g = load_golden("resize")
+    for s in (2, 4):
+        for is_flow in (0, 1):
+            (out,), (gi,) = _grads(lambda a: uu.upsample(a, bool(is_flow), scale_factor=float(s)), [g["in0"]], (0,))
+            assert_close(out, g["up%d_%d_out0_f64" % (s, is_flow)], RTOL_VALUE)
+            assert_close(gi, g["up%d_%d_grad0_f64" % (s, is_flow)], RTOL_GRAD)
+            (out,), (gi,) = _grads(lambda a: uu.downsample(a, bool(is_flow), scale_factor=float(s)), [g["in1"]], (0,))
+            assert_close(out, g["down%d_%d_out0_f64" % (s, is_flow)], RTOL_VALUE)
+            assert_close(gi, g["down%d_%d_grad0_f64" % (s, is_flow)], RTOL_GRAD)
+
+
+def test_census_golden():
+    from arflow_b200 import loss_blocks as lb
+    from arflow_b200 import uflow_utils as uu
+    g = load_golden("census")
+    a, b, m = g["in0"], g["in1"], g["in2"]
+    (loss,), (ga, gb) = _grads(lambda x, y, mm: uu.census_loss(x, y, mm), [a, b, m], (0, 1))
+    assert_close(loss, g["loss_out0_f64"], RTOL_VALUE, "census_loss")
+    assert_close(ga, g["loss_grad0_f64"], RTOL_GRAD, "d census_loss / d image_a")
+    assert_close(gb, g["loss_grad1_f64"], RTOL_GRAD, "d census_loss / d image_b")
+    (h, w), (ga, gb) = _grads(lambda x, y, mm: uu.census_loss_no_penalty(x, y, mm), [a, b, m], (0, 1))
+    assert_close(h, g["nopen_out0_f64"], RTOL_VALUE, "hamming")
+    assert_close(w, g["nopen_out1_f64"], RTOL_VALUE, "weight")
+    assert_close(ga, g["nopen_grad0_f64"], RTOL_GRAD)
+    assert_close(gb, g["nopen_grad1_f64"], RTOL_GRAD)
+    (d,), (gb,) = _grads(lambda x, y: lb.TernaryLoss(x, y, max_distance=1)[0], [a, b], (1,))
+    assert_close(d, g["tern1_out0_f64"], RTOL_VALUE)
+    assert_close(gb, g["tern1_grad1_f64"], RTOL_GRAD)
+    d3, _ = lb.TernaryLoss(a.cuda(), b.cuda(), max_distance=3, sum_dist=True)
+    assert_close(d3, g["tern3s_out0_f64"], RTOL_VALUE)
+    assert torch.equal(lb.TernaryLoss(a.cuda(), b.cuda(), max_distance=2)[1].cpu(), g["tern2mask_out0_f32"])
+    # the explicit transform helper agrees with the fused kernel
+    ham = uu.soft_hamming(uu.census_transform(a.cuda(), 7), uu.census_transform(b.cuda(), 7))
+    assert_close(ham, g["nopen_out0_f64"], RTOL_VALUE)
+
+
+def test_smooth_blocks_golden():
+    from arflow_b200 import loss_blocks as lb
+    g = load_golden("smooth_blocks")
+    flo, image = g["in0"], g["in1"]
+    for key, fn in (("s1abs", lambda f, i: lb.smooth_grad_1st(f, i, 10.0)),
+                    ("s1uf", lambda f, i: lb.smooth_grad_1st(f, i, 10.0, penalty="uflow")),
+                    ("s2", lambda f, i: lb.smooth_grad_2nd(f, i, 10.0))):
+        (out,), (gf,) = _grads(fn, [flo, image], (0,))
+        assert_close(out, g[key + "_out0_f64"], RTOL_VALUE, key)
+        assert_close(gf, g[key + "_grad0_f64"], RTOL_GRAD, key)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_uflow_loss_golden(order):
+    from arflow_b200.uflow_loss import UFlowLoss
+    g = load_golden("uflow_loss_order%d" % order)
+    cfg = types.SimpleNamespace(edge_constant=150, w_smooth=4.0, w_census=1.0, with_bk=True, smooth_order=order)
+    ins = [g["in0"], g["in1"], g["in2"], g["in3"]]
+    outs, (g0, g2) = _grads(lambda o0, o1, o2, t: UFlowLoss(cfg)([o0, o1, o2], t), ins, (0, 2))
+    # the parity target of the warp inside the loss is the fp32 grid_sample path (see test_warp_gpu._check)
+    for k in range(4):
+        assert_close(outs[k], g["out%d_f32" % k], RTOL_VALUE, "output %d" % k)
+    assert_close(outs[4], g["out4_f32"], 1e-4, "mask1")
+    assert_close(g0, g["grad0_f32"], RTOL_GRAD, "d/d output[0]")
+    assert_close(g2, g["grad2_f32"], RTOL_GRAD, "d/d output[2]")
+    assert_close(outs[0], g["out0_f64"], 1e-4, "total vs float64")
+
+
+def test_uflow_loss_full_size_vs_oracle(oracle):
+    """Config-2 shape (B reduced to 2 so the oracle finishes in seconds): loss values and gradients."""
+    from arflow_b200.uflow_loss import UFlowLoss
+    gen = torch.Generator().manual_seed(21)
+    B, H, W = 2, 384, 512
+    o0 = torch.randn(B, 4, H, W, generator=gen) * 3
+    o1 = torch.randn(B, 4, H // 2, W // 2, generator=gen)
+    o2 = torch.randn(B, 4, H // 4, W // 4, generator=gen)
+    t = torch.rand(B, 6, H, W, generator=gen)
+    cfg = types.SimpleNamespace(edge_constant=150, w_smooth=4.0, w_census=1.0, with_bk=True, smooth_order=1)
+    a0, a2 = o0.cuda().requires_grad_(True), o2.cuda().requires_grad_(True)
+    out = UFlowLoss(cfg)([a0, o1.cuda(), a2], t.cuda())
+    out[0].backward()
+    r0, r2 = o0.clone().requires_grad_(True), o2.clone().requires_grad_(True)
+    ref = oracle.uflow_loss([r0, o1, r2], t)
+    ref[0].backward()
+    for k in range(4):
+        assert_close(out[k], ref[k], RTOL_VALUE, "output %d" % k)
+    assert_close(a0.grad, r0.grad, RTOL_GRAD)
+    assert_close(a2.grad, r2.grad, RTOL_GRAD)

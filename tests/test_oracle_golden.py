@@ -61,3 +61,85 @@ def test_resample(oracle):
     assert_close(out, g["out0_f64"], TIGHT)
     assert_close(gx, g["grad0_f64"], TIGHT)
     assert_close(gf, g["grad1_f64"], 1e-10)
+
+
+def _w(shape):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(1234)).double()
+
+
+def _grads(fn, inputs, wrt):
+    """d sum(out*w) / d inputs[wrt], w drawn exactly like tests/golden/make_golden.py::both."""
+    ins = [i.double().clone().requires_grad_(k in wrt) for k, i in enumerate(inputs)]
+    out = fn(*ins)
+    outs = out if isinstance(out, (tuple, list)) else (out,)
+    g = torch.Generator().manual_seed(1234)
+    loss = 0
+    for o in outs:
+        if o.requires_grad:
+            loss = loss + (o * torch.randn(o.shape, generator=g).double()).sum()
+    return outs, torch.autograd.grad(loss, [ins[k] for k in wrt])
+
+
+def test_masks(oracle):
+    g = load_golden("masks")
+    flow, flow_b = g["in0"].double(), g["in1"].double()
+    assert torch.equal(oracle.mask_invalid(oracle.flow_to_warp(flow)), g["invalid_out0_f64"])
+    assert_close(oracle.range_map(flow), g["range_out0_f64"], TIGHT)
+    assert_close(oracle.range_map(flow), g["range_wu_out0_f64"], TIGHT)
+    assert_close(oracle.splat_count(oracle.flow_to_warp(flow)), g["corrmap_out0_f64"], TIGHT)
+    assert torch.equal(oracle.occu_mask_backward(flow, 0.2), g["occ_bw_out0_f64"])
+    assert_close(oracle.occu_mask_backward(flow, 0.0), g["occ_bw0_out0_f64"], 1e-7)  # reference returns .float()
+    assert torch.equal(oracle.border_mask(flow), g["border_out0_f64"])
+    assert torch.equal(oracle.occu_mask_bidirection(flow * 0.3, flow_b * 0.3), g["occ_bi_out0_f64"])
+
+
+def test_resize(oracle):
+    g = load_golden("resize")
+    for s in (2, 4):
+        for is_flow in (0, 1):
+            (out,), (gi,) = _grads(lambda a: oracle.resize_bilinear(a, float(s), bool(is_flow)), [g["in0"]], (0,))
+            assert_close(out, g["up%d_%d_out0_f64" % (s, is_flow)], TIGHT)
+            assert_close(gi, g["up%d_%d_grad0_f64" % (s, is_flow)], TIGHT)
+            (out,), (gi,) = _grads(lambda a: oracle.resize_bilinear(a, 1.0 / s, bool(is_flow)), [g["in1"]], (0,))
+            assert_close(out, g["down%d_%d_out0_f64" % (s, is_flow)], TIGHT)
+            assert_close(gi, g["down%d_%d_grad0_f64" % (s, is_flow)], TIGHT)
+
+
+def test_census(oracle):
+    g = load_golden("census")
+    a, b, m = g["in0"], g["in1"], g["in2"]
+    (loss,), (ga, gb) = _grads(lambda x, y, mm: oracle.census_loss(x, y, mm), [a, b, m], (0, 1))
+    assert_close(loss, g["loss_out0_f64"], TIGHT)
+    assert_close(ga, g["loss_grad0_f64"], 1e-10)
+    assert_close(gb, g["loss_grad1_f64"], 1e-10)
+    (h, w), (ga, gb) = _grads(lambda x, y, mm: oracle.census_loss_no_penalty(x, y, mm), [a, b, m], (0, 1))
+    assert_close(h, g["nopen_out0_f64"], TIGHT)
+    assert_close(w, g["nopen_out1_f64"], TIGHT)
+    assert_close(gb, g["nopen_grad1_f64"], 1e-10)
+    (d,), (gb,) = _grads(lambda x, y: oracle.ternary_loss(x, y, 1)[0], [a, b], (1,))
+    assert_close(d, g["tern1_out0_f64"], TIGHT)
+    assert_close(gb, g["tern1_grad1_f64"], 1e-10)
+    assert_close(oracle.ternary_loss(a.double(), b.double(), 3, True)[0], g["tern3s_out0_f64"], TIGHT)
+    assert torch.equal(oracle.ternary_loss(a.double(), b.double(), 2)[1], g["tern2mask_out0_f64"])
+
+
+def test_smooth_blocks(oracle):
+    g = load_golden("smooth_blocks")
+    flo, image = g["in0"], g["in1"]
+    for key, fn in (("s1abs", lambda f, i: oracle.smooth_grad_1st(f, i, 10.0)),
+                    ("s1uf", lambda f, i: oracle.smooth_grad_1st(f, i, 10.0, "uflow")),
+                    ("s2", lambda f, i: oracle.smooth_grad_2nd(f, i, 10.0))):
+        (out,), (gf,) = _grads(fn, [flo, image], (0,))
+        assert_close(out, g[key + "_out0_f64"], TIGHT, key)
+        assert_close(gf, g[key + "_grad0_f64"], 1e-10, key)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_uflow_loss(oracle, order):
+    g = load_golden("uflow_loss_order%d" % order)
+    ins = [g["in0"], g["in1"], g["in2"], g["in3"]]
+    outs, (g0, g2) = _grads(lambda o0, o1, o2, t: oracle.uflow_loss([o0, o1, o2], t, smooth_order=order), ins, (0, 2))
+    for k in range(5):
+        assert_close(outs[k], g["out%d_f64" % k], 1e-11, "output %d" % k)
+    assert_close(g0, g["grad0_f64"], 1e-9)
+    assert_close(g2, g["grad2_f64"], 1e-9)
