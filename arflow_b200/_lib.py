@@ -20,6 +20,7 @@ PROTOTYPES = {
     "arf_version": [],
     "arf_error_string": [c_int],
     "arf_debug_set": [c_int, c_int],
+    "arf_launch_count": [],
     "arf_corr_out_dims": [c_int] * 7 + [ctypes.POINTER(c_int)] * 3,
     "arf_corr_fwd": [_P, _P, _P] + [c_int] * 9 + [_P],
     "arf_corr_bwd": [_P, _P, _P, _P, _P] + [c_int] * 9 + [_P],
@@ -38,7 +39,7 @@ PROTOTYPES = {
     "arf_smooth_fwd": [_P] * 4 + [c_int] * 8 + [c_float] * 3 + [_P],
     "arf_smooth_bwd": [_P] * 4 + [c_int] * 8 + [c_float] * 3 + [_P],
 }
-_RESTYPES = {"arf_error_string": ctypes.c_char_p}
+_RESTYPES = {"arf_error_string": ctypes.c_char_p, "arf_launch_count": ctypes.c_longlong}
 
 _lib = None
 
@@ -91,7 +92,36 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+_profile = None   # when a list: (name, int args, start event, end event) per call, see profile_start
+
+
+def profile_start():
+    """Bracket every C-ABI call with CUDA events on the launching stream (bench.py's in-situ kernel
+    timings; not for use under CUDA-graph capture)."""
+    global _profile
+    _profile = []
+
+
+def profile_stop():
+    global _profile
+    rec, _profile = _profile, None
+    torch.cuda.synchronize()
+    return [(n, a, s.elapsed_time(e)) for (n, a, s, e) in rec]
+
+
+def launch_count():
+    return int(load().arf_launch_count())
+
+
 def call(name, *args):
     """Invoke a C-ABI entry point on the current stream and raise on failure."""
-    rc = getattr(load(), name)(*args)
+    fn = getattr(load(), name)
+    if _profile is None:
+        check(fn(*args), name)
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    rc = fn(*args)
+    e.record()
     check(rc, name)
+    _profile.append((name, args, s, e))

@@ -1,6 +1,10 @@
 // Library-level entry points of the C-ABI (version, error strings).
 #include "common.cuh"
 
+long long g_arf_launches = 0;
+
+extern "C" long long arf_launch_count(void) { return g_arf_launches; }
+
 extern "C" int arf_version(void) { return 100; }  // 0.1.0
 
 extern "C" const char* arf_error_string(int code) {

@@ -6,10 +6,14 @@
 
 #define ARF_NUM_SMS 148
 
+// number of kernels this library has launched in this process (bench.py reports it as gpu_launches)
+extern long long g_arf_launches;
+
 #define ARF_CHECK_LAUNCH()                                   \
     do {                                                     \
         cudaError_t e__ = cudaGetLastError();                \
         if (e__ != cudaSuccess) return (int)e__;             \
+        ++g_arf_launches;                                    \
     } while (0)
 
 #define ARF_REQUIRE(cond)                                    \

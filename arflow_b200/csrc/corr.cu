@@ -450,8 +450,8 @@ int launch_bwd_md4(const float* Fsrc, const float* gout, float* gin, int B, int 
         corr_bwd_md4<kSecond, false><<<grid, kBwdThreads, smem, st>>>(mF, mG, Fsrc, gout, gin, B, C, H, W, tiles_x,
                                                                       tiles_y, nsuper, inv_c);
     }
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? ARF_OK : (int)e;
+    ARF_CHECK_LAUNCH();
+    return ARF_OK;
 }
 
 int make_geom(CorrGeom& g, int B, int C, int H, int W, int pad, int ks, int md, int s1, int s2) {

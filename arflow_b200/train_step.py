@@ -1,0 +1,117 @@
+"""One UFlow training step (model forward, UFlowLoss, backward, Adam) as a replayable unit.
+
+Replaces, for the benchmark driver only, the per-step body of trainer/uflow_trainer.py:30-73 of the
+reference: same maths (PWCFlow -> flows_fw/flows_bw -> cat -> UFlowLoss -> backward -> Adam with the
+config's lr/betas/eps), restructured for the B200:
+  * gradients live in ONE flat buffer (zeroed by one memset, all-reduced in a few large NCCL calls
+    issued on a side stream as soon as a bucket's last gradient has been written, i.e. overlapped
+    with the rest of backward),
+  * no host synchronisation inside the step (the reference reads four `.item()`s and one level-
+    dropout draw per level from the host), so the whole step is captured once in a CUDA graph and
+    replayed: launch latency of the ~700 small kernels disappears.
+"""
+import torch
+import torch.distributed as dist
+
+
+class UFlowTrainStep:
+    def __init__(self, model, loss_fn, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, use_graph=True, world_size=1,
+                 n_buckets=3):
+        self.model = model
+        self.loss_fn = loss_fn
+        self.world_size = world_size
+        self.use_graph = use_graph
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        # flat gradient storage; parameter .grad tensors are views into it
+        total = sum(p.numel() for p in self.params)
+        self.flat_grad = torch.zeros(total, device=dev, dtype=self.params[0].dtype)
+        off = 0
+        self._spans = []
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat_grad[off:off + n].view_as(p)
+            self._spans.append((off, off + n))
+            off += n
+        self.optimizer = torch.optim.Adam(self.params, lr=lr, betas=betas, eps=eps,
+                                          capturable=dev.type == "cuda", fused=dev.type == "cuda")
+        # buckets over the flat buffer in REVERSE parameter order (backward produces the decoder's
+        # gradients first, the feature pyramid's last)
+        self._buckets = []
+        self._comm_stream = None
+        if world_size > 1:
+            self._comm_stream = torch.cuda.Stream(device=dev)
+            bounds = [int(round(total * k / n_buckets)) for k in range(n_buckets + 1)]
+            # snap bucket bounds to parameter boundaries
+            ends = [e for (_, e) in self._spans]
+            snapped = [0] + [min(ends, key=lambda e: abs(e - b)) for b in bounds[1:-1]] + [total]
+            snapped = sorted(set(snapped))
+            self._buckets = [(snapped[i], snapped[i + 1]) for i in range(len(snapped) - 1)]
+            self._pending = [0] * len(self._buckets)
+            self._bucket_of = []
+            for (s, e) in self._spans:
+                self._bucket_of.append(next(i for i, (bs, be) in enumerate(self._buckets) if bs <= s < be))
+            self._counts = [self._bucket_of.count(i) for i in range(len(self._buckets))]
+            for idx, p in enumerate(self.params):
+                p.register_post_accumulate_grad_hook(self._make_hook(self._bucket_of[idx]))
+        self._graph = None
+        self.launches_per_step = None
+        self._static_in = None
+        self._static_out = None
+
+    # ---------------------------------------------------------------- gradient all-reduce
+    def _make_hook(self, b):
+        def hook(_param):
+            self._pending[b] -= 1
+            if self._pending[b] == 0:
+                self._launch_allreduce(b)
+        return hook
+
+    def _launch_allreduce(self, b):
+        s, e = self._buckets[b]
+        cur = torch.cuda.current_stream()
+        self._comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self._comm_stream):
+            dist.all_reduce(self.flat_grad[s:e], op=dist.ReduceOp.AVG)
+
+    # ---------------------------------------------------------------- the step
+    def _step_impl(self, img_pair):
+        self.flat_grad.zero_()
+        if self.world_size > 1:
+            self._pending = list(self._counts)
+        res = self.model(img_pair, with_bk=True)
+        flows = [torch.cat([a, b], 1) for a, b in zip(res['flows_fw'], res['flows_bw'])]
+        loss, l_ph, l_sm, flow_mean, _ = self.loss_fn(flows, img_pair)
+        loss.backward()
+        if self.world_size > 1:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+        self.optimizer.step()
+        return torch.stack([loss.detach(), l_ph.detach(), l_sm.detach(), flow_mean.detach()])
+
+    def capture(self, example, warmup=3):
+        """Warm up on a side stream (cuDNN autotune, Adam state, NCCL) and capture the step."""
+        self._static_in = example.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._step_impl(self._static_in)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        from . import _lib
+        self._graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self._graph):
+            self._static_out = self._step_impl(self._static_in)
+        self.launches_per_step = _lib.launch_count() - n0   # arflow_b200 kernels inside one replay
+        torch.cuda.synchronize()
+
+    def __call__(self, img_pair):
+        """img_pair: (B,6,H,W) device tensor.  Returns a 4-vector [loss, l_ph, l_sm, mean|flow|] on the device."""
+        if not self.use_graph:
+            return self._step_impl(img_pair)
+        if self._graph is None:
+            self.capture(img_pair)
+        self._static_in.copy_(img_pair, non_blocking=True)
+        self._graph.replay()
+        return self._static_out

@@ -1,0 +1,241 @@
+"""PWCFlow — the UFlow PWC network that calls the hot path (drop-in for models/uflow_model.py).
+
+The module tree and parameter names are the reference's (`_refine_model`, `_flow_layers`,
+`_context_up_layers`, `_feature_pyramid_extractor._convs`), so a reference state_dict loads by name.
+Convolutions stay on cuDNN (out of scope); what changes is everything between them:
+  * warp / cost volume / x2 upsampling go through the arflow_b200 kernels,
+  * `forward` can run both flow directions as ONE pass over a 2B batch (`stack_directions=True`):
+    the two `forward_2_frames` calls of the reference (uflow_model.py:255-257) are independent and
+    every op is per-sample, so the result is identical while every kernel sees twice the work,
+  * level dropout is drawn on the device (no `.item()` host sync, uflow_model.py:211-214), one
+    Bernoulli per direction and level exactly like the reference's two sequential calls, which keeps
+    the step capturable in a CUDA graph.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as func
+
+
+class _CudaOps:
+    """The hot-path ops the network needs; the oracle provides a CPU twin for the baseline leg."""
+
+    def __init__(self):
+        from . import correlation, uflow_utils
+        self.flow_to_warp = uflow_utils.flow_to_warp
+        self.resample = uflow_utils.resample
+        self.upsample = uflow_utils.upsample
+        self.compute_cost_volume = correlation.compute_cost_volume
+
+
+def normalize_features(feature_list, normalize, center, moments_across_channels, moments_across_images):
+    """uflow_model.py:8-50 — per-sample moments (unbiased variance), optionally shared by the images."""
+    dim = [1, 2, 3] if moments_across_channels else [2, 3]
+    stats = [torch.var_mean(f, dim=dim, keepdim=True) for f in feature_list]
+    variances = [s[0] for s in stats]
+    means = [s[1] for s in stats]
+    if moments_across_images:
+        n = float(len(feature_list))
+        mean_all = sum(means) / n
+        var_all = sum(variances) / n
+        means = [mean_all] * len(means)
+        variances = [var_all] * len(variances)
+    stds = [torch.sqrt(v + 1e-16) for v in variances]
+    if center:
+        feature_list = [f - m for f, m in zip(feature_list, means)]
+    if normalize:
+        feature_list = [f / s for f, s in zip(feature_list, stds)]
+    return feature_list
+
+
+def compute_cost_volume(features1, features2, max_displacement):
+    """uflow_model.py:53-92."""
+    from .correlation import compute_cost_volume as _cv
+    return _cv(features1, features2, max_displacement)
+
+
+class PWCFeaturePyramid(nn.Module):
+    """uflow_model.py:364-470 — five levels of three 3x3 convolutions, the first of each with stride 2."""
+
+    def __init__(self, leaky_relu_alpha=0.1, filters=None, level1_num_layers=3, level1_num_filters=32,
+                 level1_num_1x1=0, original_layer_sizes=False, num_levels=5, channel_multiplier=1.,
+                 pyramid_resolution='half', num_channels=3):
+        super().__init__()
+        self._channel_multiplier = channel_multiplier
+        if num_levels > 6:
+            raise NotImplementedError('Max number of pyramid levels is 6')
+        if filters is None:
+            if original_layer_sizes:
+                filters = ((3, 16), (3, 32), (3, 64), (3, 96), (3, 128), (3, 196))[:num_levels]
+            else:
+                filters = ((level1_num_layers, level1_num_filters),) + ((3, 32),) * 5
+                filters = filters[:num_levels]
+        assert filters and all(len(t) == 2 and t[0] > 0 for t in filters)
+        self._leaky_relu_alpha = leaky_relu_alpha
+        self._level1_num_1x1 = level1_num_1x1
+        self._convs = nn.ModuleList()
+        c = num_channels
+        for level, (num_layers, num_filters) in enumerate(filters):
+            group = nn.ModuleList()
+            for i in range(num_layers):
+                stride = 2 if (i == 0 or (i == 1 and level == 0 and pyramid_resolution == 'quarter')) else 1
+                is3 = level > 0 or i < num_layers - level1_num_1x1
+                out_c = int(num_filters * channel_multiplier)
+                # explicit zero pad + 'valid' conv of the reference == padding=1 for the 3x3 layers
+                group.append(nn.Conv2d(c, out_c, kernel_size=(3, 3) if is3 else (1, 1), stride=stride,
+                                       padding=1 if is3 else 0))
+                c = out_c
+            self._convs.append(group)
+
+    def forward(self, x, split_features_by_sample=False):
+        x = x * 2. - 1.
+        features = []
+        for group in self._convs:
+            for conv in group:
+                x = func.leaky_relu(conv(x), negative_slope=self._leaky_relu_alpha)
+            features.append(x)
+        if split_features_by_sample:
+            n = len(features[0])
+            features = [[f[i:i + 1] for f in features] for i in range(n)]
+        return features
+
+
+class PWCFlow(nn.Module):
+    """uflow_model.py:96-362.  cfg needs `level_dropout` and `feature_norm`."""
+
+    def __init__(self, cfg, ops=None, stack_directions=True):
+        super().__init__()
+        self._ops = ops if ops is not None else _CudaOps()
+        self._stack_directions = stack_directions
+        self._leaky_relu_alpha = 0.1
+        self._drop_out_rate = cfg.level_dropout
+        self._num_context_up_channels = 32
+        self._num_levels = 5
+        self._normalize_before_cost_volume = cfg.feature_norm
+        self._channel_multiplier = 1
+        self._accumulate_flow = True
+
+        self._refine_model = self._build_refinement_model()
+        self._flow_layers = self._build_flow_layers()
+        self._context_up_layers = nn.ModuleList(
+            [nn.ConvTranspose2d(self._num_context_up_channels, self._num_context_up_channels, kernel_size=(4, 4),
+                                stride=2, padding=1) for _ in range(self._num_levels)])
+        self._feature_pyramid_extractor = PWCFeaturePyramid()
+
+    # ------------------------------------------------------------------ construction
+    def _build_flow_layers(self):
+        result = nn.ModuleList([None])  # no flow is estimated at level 0
+        block_layers = [128, 128, 96, 64, 32]
+        for i in range(1, self._num_levels):
+            layers = nn.ModuleList()
+            c_in = 81 + 32
+            if i != self._num_levels - 1:
+                c_in += 2 + self._num_context_up_channels
+            for c in block_layers:
+                layers.append(nn.Sequential(nn.Conv2d(c_in, c, kernel_size=(3, 3), stride=1, padding='same'),
+                                            nn.LeakyReLU(negative_slope=self._leaky_relu_alpha)))
+                c_in += c
+            layers.append(nn.Conv2d(block_layers[-1], 2, kernel_size=(3, 3), padding='same'))
+            result.append(layers)
+        return result
+
+    def _build_refinement_model(self):
+        layers = []
+        c_in = 32 + 2
+        for c, d in [(128, 1), (128, 2), (128, 4), (96, 8), (64, 16), (32, 1)]:
+            layers.append(nn.Conv2d(c_in, c, kernel_size=(3, 3), stride=1, padding='same', dilation=d))
+            layers.append(nn.LeakyReLU(negative_slope=self._leaky_relu_alpha))
+            c_in = c
+        layers.append(nn.Conv2d(c_in, 2, kernel_size=(3, 3), stride=1, padding='same'))
+        return nn.ModuleList(layers)
+
+    def init_weights(self, xavier=False):
+        """uflow_model.py:124-136.  The reference iterates `self.named_modules()` — (name, module) tuples —
+        so its isinstance checks never match and the call leaves PyTorch's default (Kaiming-uniform)
+        initialisation in place.  That observable behaviour is kept; `xavier=True` applies what the
+        reference's code evidently intended (Xavier-uniform weights, zero biases)."""
+        if not xavier:
+            return
+        for layer in self.modules():
+            if isinstance(layer, (nn.Conv2d, nn.ConvTranspose2d)):
+                nn.init.xavier_uniform_(layer.weight)
+                if layer.bias is not None:
+                    nn.init.constant_(layer.bias, 0)
+
+    # ------------------------------------------------------------------ forward
+    def _keep(self, like, groups):
+        """Level-dropout multiplier: one Bernoulli per direction (`groups`), broadcast over its samples."""
+        if not (self.training and self._drop_out_rate > 0):
+            return None
+        keep = (torch.rand(groups, device=like.device) > self._drop_out_rate).to(like.dtype)
+        return keep.repeat_interleave(like.shape[0] // groups).view(-1, 1, 1, 1)
+
+    def forward_2_frames(self, feature_pyramid1, feature_pyramid2, groups=1):
+        ops = self._ops
+        context = flow = flow_up = context_up = None
+        flows = []
+        for level in range(self._num_levels - 1, 0, -1):
+            features1, features2 = feature_pyramid1[level], feature_pyramid2[level]
+            if flow_up is None:
+                warped2 = features2
+            else:
+                warped2 = ops.resample(features2, ops.flow_to_warp(flow_up))
+            f1n, w2n = normalize_features([features1, warped2], normalize=self._normalize_before_cost_volume,
+                                          center=self._normalize_before_cost_volume, moments_across_channels=True,
+                                          moments_across_images=True)
+            cost_volume = func.leaky_relu(ops.compute_cost_volume(f1n, w2n, max_displacement=4),
+                                          negative_slope=self._leaky_relu_alpha)
+            if flow_up is None:
+                x_in = torch.cat([cost_volume, features1], dim=1)
+            elif context_up is None:
+                x_in = torch.cat([flow_up, cost_volume, features1], dim=1)
+            else:
+                x_in = torch.cat([context_up, flow_up, cost_volume, features1], dim=1)
+            flow_layers = self._flow_layers[level]
+            x_out = None
+            for layer in list(flow_layers)[:-1]:
+                x_out = layer(x_in)
+                x_in = torch.cat([x_in, x_out], dim=1)
+            context = x_out
+            flow = flow_layers[-1](context)
+
+            keep = self._keep(flow, groups)
+            if keep is not None:
+                context = context * keep
+                flow = flow * keep
+            if flow_up is not None and self._accumulate_flow:
+                flow = flow + flow_up
+            flow_up = ops.upsample(flow, is_flow=True)
+            context_up = self._context_up_layers[level](context)
+            flows.insert(0, flow)
+
+        refinement = torch.cat([context, flow], dim=1)
+        for layer in self._refine_model:
+            refinement = layer(refinement)
+        keep = self._keep(refinement, groups)
+        if keep is not None:
+            refinement = refinement * keep
+        flows[0] = flow + refinement
+        flows.insert(0, ops.upsample(flows[0], is_flow=True))
+        flows.insert(0, ops.upsample(flows[0], is_flow=True))
+        return flows
+
+    def forward(self, x, with_bk=True):
+        n_frames = x.size(1) // 3
+        if n_frames != 2:
+            raise NotImplementedError
+        B = x.shape[0]
+        res_dict = {}
+        if with_bk and self._stack_directions:
+            # one pyramid pass over [img1; img2], one decoder pass over [(1,2); (2,1)]
+            feats = self._feature_pyramid_extractor(torch.cat([x[:, 0:3], x[:, 3:6]], dim=0))
+            p1 = feats
+            p2 = [torch.cat([f[B:], f[:B]], dim=0) for f in feats]
+            flows = self.forward_2_frames(p1, p2, groups=2)
+            res_dict['flows_fw'] = [f[:B] for f in flows]
+            res_dict['flows_bw'] = [f[B:] for f in flows]
+            return res_dict
+        pyr = [self._feature_pyramid_extractor(x[:, 3 * i: 3 * i + 3]) for i in range(2)]
+        res_dict['flows_fw'] = self.forward_2_frames(pyr[0], pyr[1])
+        if with_bk:
+            res_dict['flows_bw'] = self.forward_2_frames(pyr[1], pyr[0])
+        return res_dict

@@ -56,6 +56,8 @@ extern "C" {
 
 int         arf_version(void);
 const char* arf_error_string(int code);
+/* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
+long long   arf_launch_count(void);
 /* Test hook. key 0: value != 0 forces the non-TMA (cp.async) staging path of the tiled kernels. */
 int         arf_debug_set(int key, int value);
 

@@ -73,14 +73,15 @@ def corr_bwd_c(f1, f2, gout, pad=4, ks=1, md=4, s1=1, s2=1):
 
 
 def cost_volume(f1, f2, md=4):
-    """correlation_native.py:13-23 == uflow_model.py:53-92 (pad=md, ks=1, strides 1), vectorised:
-    one unfold of the zero-padded f2 instead of 81 slice-multiply-mean passes.  Differentiable, so
-    it also is the CPU baseline for forward+backward."""
+    """correlation_native.py:13-23 == uflow_model.py:53-92 (pad=md, ks=1, strides 1): one plane per
+    displacement (dy slow, dx fast), each the channel mean of f1 times the shifted, zero-padded f2.
+    Differentiable; this is the CPU baseline for forward+backward (as fast as the reference's own loop —
+    an unfold-based single-op version measured 3.5x slower on 8 cores)."""
     B, C, H, W = f1.shape
     D = 2 * md + 1
     f2p = F.pad(f2, (md, md, md, md))
-    win = f2p.unfold(2, H, 1).unfold(3, W, 1)          # B, C, D, D, H, W   (dy, dx leading)
-    return (f1[:, :, None, None] * win).mean(dim=1).reshape(B, D * D, H, W)
+    planes = [(f1 * f2p[:, :, dy:dy + H, dx:dx + W]).mean(1) for dy in range(D) for dx in range(D)]
+    return torch.stack(planes, 1)
 
 
 # --------------------------------------------------------------------------- warp -----------
@@ -346,3 +347,49 @@ def uflow_loss(output, target, w_census=1.0, w_smooth=4.0, edge_constant=150.0, 
         loss_smooth = loss_smooth + smooth_uflow(resize_bilinear(im2, 0.25, False), f21_2, edge_constant, w_smooth,
                                                  smooth_order)
     return loss_warp + loss_smooth, loss_warp, loss_smooth, output[0].abs().mean(), mask1
+
+
+# --------------------------------------------------------------------------- CPU train step -
+class OracleOps:
+    """CPU twins of the ops arflow_b200.uflow_model.PWCFlow calls (its `ops` argument)."""
+    flow_to_warp = staticmethod(flow_to_warp)
+
+    @staticmethod
+    def resample(source, coords):
+        return warp(source, coords, kind="coords")
+
+    @staticmethod
+    def upsample(img, is_flow, scale_factor=2.0):
+        return resize_bilinear(img, scale_factor, is_flow)
+
+    @staticmethod
+    def compute_cost_volume(f1, f2, max_displacement):
+        return cost_volume(f1, f2, max_displacement)
+
+
+class CpuTrainStep:
+    """The reference's chairs_uflow training step restated on the CPU (PWCFlow + UFlowLoss + Adam,
+    trainer/uflow_trainer.py:30-73, configs/chairs_uflow.json) with the oracle's hot-path ops: the
+    baseline bench.py times beside the B200 numbers.  The network definition (plain nn.Conv2d layers)
+    is shared with the product; the hot path is not."""
+
+    def __init__(self, level_dropout=0.1, feature_norm=True, smooth_order=1, lr=1e-4, seed=0):
+        import types
+        from arflow_b200.uflow_model import PWCFlow
+        torch.manual_seed(seed)
+        cfg = types.SimpleNamespace(level_dropout=level_dropout, feature_norm=feature_norm)
+        self.model = PWCFlow(cfg, ops=OracleOps(), stack_directions=False)
+        self.model.init_weights()   # no-op, like the reference's
+        self.model.train()
+        self.smooth_order = smooth_order
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-8)
+
+    def __call__(self, img_pair):
+        res = self.model(img_pair, with_bk=True)
+        flows = [torch.cat([a, b], 1) for a, b in zip(res['flows_fw'], res['flows_bw'])]
+        out = uflow_loss(flows, img_pair, w_census=1.0, w_smooth=4.0, edge_constant=150.0, with_bk=True,
+                         smooth_order=self.smooth_order)
+        self.opt.zero_grad()
+        out[0].backward()
+        self.opt.step()
+        return float(out[0].detach())

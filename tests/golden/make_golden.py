@@ -161,6 +161,22 @@ def main():
         res = both(lambda o0, o1, o2, t: UFlowLoss(cfg)([o0, o1, o2], t), out0, out1, out2, target, grads=(0, 2))
         save("uflow_loss_order%d" % order, (out0, out1, out2, target), res)
 
+    # ---- PWCFlow network (structure check of the caller): eval mode, seeded Xavier init ----
+    from models.uflow_model import PWCFlow
+    cfg = EasyDict(level_dropout=0.1, feature_norm=True)
+    torch.manual_seed(123)          # weights = PyTorch default init in construction order
+    net = PWCFlow(cfg)
+    net.init_weights()              # a no-op in the reference (iterates (name, module) tuples)
+    net.eval()
+    pair = torch.rand(1, 6, 192, 256, generator=torch.Generator().manual_seed(77))   # regenerated by the test
+    with torch.no_grad():
+        r = net(pair, with_bk=True)
+    n_par = sum(p.numel() for p in net.parameters())
+    save("pwcflow_eval", (np.asarray(77),), {"fw2": r["flows_fw"][2].numpy(), "bw2": r["flows_bw"][2].numpy(),
+                                   "fw0_mean": np.asarray(r["flows_fw"][0].abs().mean().item()),
+                                   "n_params": np.asarray(n_par),
+                                   "keys": np.asarray(list(net.state_dict().keys()))})
+
 
 if __name__ == "__main__":
     torch.manual_seed(0)

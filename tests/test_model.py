@@ -1,0 +1,86 @@
+"""The PWCFlow caller: same module tree / state-dict keys / outputs as the reference network."""
+import types
+
+import pytest
+import torch
+
+from conftest import assert_close, load_golden
+import numpy as np
+import os
+from conftest import GOLDEN
+
+
+def _golden():
+    with np.load(os.path.join(GOLDEN, "pwcflow_eval.npz"), allow_pickle=False) as z:
+        return {k: z[k] for k in z.files}
+
+
+def _build(ops=None, device="cpu", stack=True):
+    from arflow_b200.uflow_model import PWCFlow
+    cfg = types.SimpleNamespace(level_dropout=0.1, feature_norm=True)
+    torch.manual_seed(123)
+    net = PWCFlow(cfg, ops=ops, stack_directions=stack)
+    net.init_weights()
+    return net.to(device).eval()
+
+
+def _input(g):
+    return torch.rand(1, 6, 192, 256, generator=torch.Generator().manual_seed(int(g["in0"])))
+
+
+def test_state_dict_keys_and_size_match_reference(oracle):
+    g = _golden()
+    net = _build(ops=oracle.OracleOps())
+    assert [str(k) for k in g["keys"]] == list(net.state_dict().keys())
+    assert int(g["n_params"]) == sum(p.numel() for p in net.parameters()) == 5734634
+
+
+@pytest.mark.parametrize("stack", [False, True])
+def test_forward_matches_reference_on_cpu_ops(oracle, stack):
+    g = _golden()
+    net = _build(ops=oracle.OracleOps(), stack=stack)
+    with torch.no_grad():
+        r = net(_input(g), with_bk=True)
+    assert_close(r["flows_fw"][2], torch.from_numpy(g["fw2"]), 1e-4, "flows_fw[2]")
+    assert_close(r["flows_bw"][2], torch.from_numpy(g["bw2"]), 1e-4, "flows_bw[2]")
+    assert abs(float(r["flows_fw"][0].abs().mean()) - float(g["fw0_mean"])) < 1e-4 * float(g["fw0_mean"])
+
+
+@pytest.mark.gpu
+def test_forward_matches_reference_on_b200():
+    g = _golden()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False      # compare against an fp32 CPU run of the reference
+    try:
+        net = _build(device="cuda")
+        with torch.no_grad():
+            r = net(_input(g).cuda(), with_bk=True)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert_close(r["flows_fw"][2], torch.from_numpy(g["fw2"]), 1e-3, "flows_fw[2]")
+    assert_close(r["flows_bw"][2], torch.from_numpy(g["bw2"]), 1e-3, "flows_bw[2]")
+
+
+@pytest.mark.gpu
+def test_train_step_graph_matches_eager():
+    """CUDA-graph replay and eager execution of the train step give the same losses (level dropout off)."""
+    from arflow_b200.train_step import UFlowTrainStep
+    from arflow_b200.uflow_loss import UFlowLoss
+    from arflow_b200.uflow_model import PWCFlow
+    lcfg = types.SimpleNamespace(edge_constant=150, w_smooth=4.0, w_census=1.0, with_bk=True, smooth_order=1)
+    x = torch.rand(2, 6, 192, 256, generator=torch.Generator().manual_seed(5)).cuda()
+    losses = []
+    for use_graph in (False, True):
+        torch.manual_seed(7)
+        net = PWCFlow(types.SimpleNamespace(level_dropout=0.0, feature_norm=True)).cuda()
+        net.init_weights()
+        net.train()
+        step = UFlowTrainStep(net, UFlowLoss(lcfg), use_graph=use_graph)
+        if use_graph:
+            step.capture(x, warmup=0)
+            assert step.launches_per_step > 20
+        out = [step(x).clone() for _ in range(3)]
+        losses.append(torch.stack(out).cpu())
+    assert torch.isfinite(losses[0]).all()
+    assert_close(losses[1][:, 0], losses[0][:, 0], 1e-3, "loss trajectory graph vs eager")
+    assert float(losses[0][2, 0]) != float(losses[0][0, 0])   # parameters are being updated
