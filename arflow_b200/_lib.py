@@ -38,6 +38,10 @@ PROTOTYPES = {
     "arf_smooth_num_partials": [c_int] * 3,
     "arf_smooth_fwd": [_P] * 4 + [c_int] * 8 + [c_float] * 3 + [_P],
     "arf_smooth_bwd": [_P] * 4 + [c_int] * 8 + [c_float] * 3 + [_P],
+    "arf_stencil_mv_fwd": [_P, _P, _P] + [c_int] * 5 + [_P],
+    "arf_stencil_mv_bwd": [_P] * 5 + [c_int] * 5 + [_P],
+    "arf_trisolve": [_P] * 6 + [ctypes.c_longlong, c_int, c_int, c_int, _P],
+    "arf_inv_diag": [_P] * 4 + [ctypes.c_longlong, c_int, c_int, _P],
 }
 _RESTYPES = {"arf_error_string": ctypes.c_char_p, "arf_launch_count": ctypes.c_longlong}
 

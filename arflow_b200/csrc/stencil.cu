@@ -1,0 +1,244 @@
+// Stencil-triangular algebra of the non-diagonal ELBO losses.
+//
+// T1/T2  y = L x and y = L^T x for the lower-triangular stencil matrix with (k+1)^2 taps per flow
+//        channel (utils/triag_solve.py:29-43, 59-73): HBM-bound streaming kernels, every coefficient
+//        is read exactly once; the backward pass produces dX and all tap gradients in one sweep.
+// T3     forward / backward substitution for the k=1 stencil (triag_solve_cuda.cu:7-69).  The reference
+//        runs one THREAD per system through M*N serial global-memory updates.  Here one CTA per system
+//        walks the M+N-1 anti-diagonals: thread <-> row, the three previous values a cell needs come
+//        from the thread's own register (left) and its upper neighbour's last two values (shared
+//        memory), coefficients for the next diagonal are prefetched while the current one is solved.
+// T4     diag((L L^T)^-1) (triag_solve_cuda.cu:72-139): one CTA per (system, start pixel) runs the same
+//        wavefront on the sub-rectangle below/right of the start pixel and reduces the squares.
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------- mat-vec -----
+// transposed = 0:  Y[p] = sum_t A[t][p - o_t] * X[p - o_t]        (o_t = (i,j), inside the image)
+// transposed = 1:  Y[p] = sum_t A[t][p]       * X[p + o_t]
+__global__ void __launch_bounds__(256)
+stencil_mv_kernel(const float* __restrict__ A, const float* __restrict__ X, float* __restrict__ Y, int N, int H,
+                  int W, int k, int transposed) {
+    const size_t hw = (size_t)H * W;
+    const int k1 = k + 1;
+    const long long total = (long long)N * 2 * hw;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int x = idx % W;
+        long long t = idx / W;
+        int y = t % H; t /= H;
+        int ch = t & 1;
+        long long n = t >> 1;
+        const float* An = A + n * 2 * k1 * k1 * hw + ch * hw;
+        const float* Xn = X + (n * 2 + ch) * hw;
+        float acc = 0.f;
+        for (int i = 0; i < k1; ++i)
+            for (int j = 0; j < k1; ++j) {
+                int tap = i * k1 + j;
+                if (!transposed) {
+                    int ys = y - i, xs = x - j;
+                    if (ys >= 0 && xs >= 0) {
+                        size_t o = (size_t)ys * W + xs;
+                        acc = fmaf(__ldg(An + (size_t)tap * 2 * hw + o), __ldg(Xn + o), acc);
+                    }
+                } else {
+                    // the reference slices A[..., 0:-i, 0:-j]: the tap exists where p + o stays inside
+                    int ys = y + i, xs = x + j;
+                    if (ys < H && xs < W)
+                        acc = fmaf(__ldg(An + (size_t)tap * 2 * hw + (size_t)y * W + x), __ldg(Xn + (size_t)ys * W + xs), acc);
+                }
+            }
+        Y[idx] = acc;
+    }
+}
+
+// Backward of both products in one sweep over A:
+//   transposed = 0 (y = L x):    dX[p] = sum_t A[t][p] * gY[p + o_t],    dA[t][p] = X[p] * gY[p + o_t]
+//   transposed = 1 (y = L^T x):  dX[p] = sum_t A[t][p - o_t] * gY[p - o_t],  dA[t][p] = gY[p] * X[p + o_t]
+__global__ void __launch_bounds__(256)
+stencil_mv_bwd_kernel(const float* __restrict__ A, const float* __restrict__ X, const float* __restrict__ gY,
+                      float* __restrict__ dA, float* __restrict__ dX, int N, int H, int W, int k, int transposed) {
+    const size_t hw = (size_t)H * W;
+    const int k1 = k + 1;
+    const long long total = (long long)N * 2 * hw;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int x = idx % W;
+        long long t = idx / W;
+        int y = t % H; t /= H;
+        int ch = t & 1;
+        long long n = t >> 1;
+        const size_t p = (size_t)y * W + x;
+        const float* An = A + n * 2 * k1 * k1 * hw + ch * hw;
+        float* dAn = dA ? dA + n * 2 * k1 * k1 * hw + ch * hw : nullptr;
+        const float* Xn = X + (n * 2 + ch) * hw;
+        const float* Gn = gY + (n * 2 + ch) * hw;
+        const float xp = __ldg(Xn + p), gp = __ldg(Gn + p);
+        float acc = 0.f;
+        for (int i = 0; i < k1; ++i)
+            for (int j = 0; j < k1; ++j) {
+                const size_t to = (size_t)(i * k1 + j) * 2 * hw;
+                if (!transposed) {
+                    bool in = (y + i < H) && (x + j < W);
+                    float g = in ? __ldg(Gn + p + (size_t)i * W + j) : 0.f;
+                    if (dX) acc = fmaf(__ldg(An + to + p), g, acc);
+                    if (dAn) dAn[to + p] = xp * g;
+                } else {
+                    bool in = (y + i < H) && (x + j < W);
+                    if (dAn) dAn[to + p] = in ? gp * __ldg(Xn + p + (size_t)i * W + j) : 0.f;
+                    if (dX && y - i >= 0 && x - j >= 0) {
+                        size_t o = p - (size_t)i * W - j;
+                        acc = fmaf(__ldg(An + to + o), __ldg(Gn + o), acc);
+                    }
+                }
+            }
+        if (dX) dX[idx] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------- wavefront ---
+// Solves the stencil system on the rectangle rows [r_lo, M), cols [c_lo, N) of one (M x N) system,
+// sweeping anti-diagonals.  Lower (forward substitution, triag_solve.py:76-94):
+//   Y[i,j] = (X[i,j] - C[i-1,j] Y[i-1,j] - B[i,j-1] Y[i,j-1] - D[i-1,j-1] Y[i-1,j-1]) / A[i,j]
+// Upper (back substitution, :97-115) is the same recurrence on the point-reflected grid with the
+// coefficients taken at (i,j) instead of the predecessor:
+//   Y[i,j] = (X[i,j] - C[i,j] Y[i+1,j] - B[i,j] Y[i,j+1] - D[i,j] Y[i+1,j+1]) / A[i,j]
+// Thread t owns logical row t (rows are processed in logical coordinates li = i - r_lo or reflected).
+// unit_rhs: X = e_(r_lo,c_lo) (inverse-diagonal mode), Y is not stored, the sum of squares is returned.
+// Block size = rows rounded up to a warp; sY holds the last two diagonals: sY[2][blockDim.x + 1].
+template <bool kUpper, bool kUnit>
+__device__ float wavefront(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ C,
+                           const float* __restrict__ D, const float* __restrict__ X, float* __restrict__ Y, int M,
+                           int N, int r_lo, int c_lo, float* sY) {
+    const int rows = M - r_lo, cols = N - c_lo;
+    const int t = threadIdx.x;                 // logical row
+    const int stride = blockDim.x + 1;
+    // physical coordinates of logical (li, lj)
+    auto pi = [&](int li) { return kUpper ? M - 1 - li : r_lo + li; };
+    auto pj = [&](int lj) { return kUpper ? N - 1 - lj : c_lo + lj; };
+    // upper solves always cover the whole grid in this library (r_lo = c_lo = 0)
+    float left = 0.f;                          // Y[li][lj-1], own previous value
+    float sumsq = 0.f;
+    sY[t + 1] = 0.f;
+    sY[stride + t + 1] = 0.f;
+    if (t == 0) { sY[0] = 0.f; sY[stride] = 0.f; }
+    __syncthreads();
+
+    // prefetch for the first cell of this row
+    float a = 1.f, b = 0.f, c = 0.f, d = 0.f, x = 0.f;
+    auto fetch = [&](int lj) {
+        if (t < rows && lj >= 0 && lj < cols) {
+            const int i = pi(t), j = pj(lj);
+            a = __ldg(A + (size_t)i * N + j);
+            x = kUnit ? ((t == 0 && lj == 0) ? 1.f : 0.f) : __ldg(X + (size_t)i * N + j);
+            if (!kUpper) {
+                b = lj > 0 ? __ldg(B + (size_t)i * (N - 1) + (j - 1)) : 0.f;
+                c = t > 0 ? __ldg(C + (size_t)(i - 1) * N + j) : 0.f;
+                d = (t > 0 && lj > 0 && D) ? __ldg(D + (size_t)(i - 1) * (N - 1) + (j - 1)) : 0.f;
+            } else {
+                b = lj > 0 ? __ldg(B + (size_t)i * (N - 1) + j) : 0.f;
+                c = t > 0 ? __ldg(C + (size_t)i * N + j) : 0.f;
+                d = (t > 0 && lj > 0 && D) ? __ldg(D + (size_t)i * (N - 1) + j) : 0.f;
+            }
+        }
+    };
+    fetch(0 - t);
+    const int ndiag = rows + cols - 1;
+    for (int dg = 0; dg < ndiag; ++dg) {
+        const int lj = dg - t;
+        const bool live = t < rows && lj >= 0 && lj < cols;
+        float* cur = sY + (dg & 1) * stride;           // receives diagonal dg
+        const float* prev = sY + ((dg + 1) & 1) * stride;  // diagonal dg-1 ... and, before overwrite, dg-2 lives in cur
+        float y = 0.f;
+        float up = 0.f, upleft = 0.f;
+        if (live) {
+            up = prev[t];          // row t-1 on diagonal dg-1  -> Y[li-1][lj]      (slot t holds row t-1)
+            upleft = cur[t];       // row t-1 on diagonal dg-2  -> Y[li-1][lj-1]
+        }
+        const float ca = a, cb = b, cc = c, cd = d, cx = x;
+        fetch(lj + 1);             // coefficients of the next diagonal: latency overlaps the solve below
+        __syncthreads();           // everyone has read diagonal dg-2 from `cur`
+        if (live) {
+            y = (((cx - cc * up) - cb * left) - cd * upleft) / ca;
+            left = y;
+            if (!kUnit) Y[(size_t)pi(t) * N + pj(lj)] = y;
+            sumsq = fmaf(y, y, sumsq);
+        }
+        cur[t + 1] = live ? y : 0.f;
+        __syncthreads();
+    }
+    return sumsq;
+}
+
+template <bool kUpper>
+__global__ void trisolve_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ C,
+                                const float* __restrict__ D, const float* __restrict__ X, float* __restrict__ Y, int M,
+                                int N) {
+    extern __shared__ float sY[];
+    const size_t s = blockIdx.x;
+    wavefront<kUpper, false>(A + s * M * N, B + s * M * (N - 1), C + s * (M - 1) * N,
+                             D ? D + s * (M - 1) * (N - 1) : nullptr, X + s * M * N, Y + s * M * N, M, N, 0, 0, sY);
+}
+
+__global__ void inv_diag_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ C,
+                                float* __restrict__ Hout, int M, int N) {
+    extern __shared__ float sY[];
+    __shared__ float red[32];
+    const size_t cell = blockIdx.x;            // (system, k, l)
+    const size_t s = cell / ((size_t)M * N);
+    const int kl = cell % ((size_t)M * N);
+    const int k = kl / N, l = kl % N;
+    float v = wavefront<false, true>(A + s * M * N, B + s * M * (N - 1), C + s * (M - 1) * N, nullptr, nullptr, nullptr,
+                                     M, N, k, l, sY);
+    v = arf_block_sum(v, red);
+    if (threadIdx.x == 0) Hout[cell] = v;
+}
+
+}  // namespace
+
+extern "C" int arf_stencil_mv_fwd(const float* A, const float* X, float* Y, int N, int H, int W, int k,
+                                  int transposed, void* stream) {
+    ARF_REQUIRE(A && X && Y && N > 0 && H > 0 && W > 0 && k >= 0 && k <= 15);
+    long long total = (long long)N * 2 * H * W;
+    stencil_mv_kernel<<<arf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(A, X, Y, N, H, W, k, transposed ? 1 : 0);
+    ARF_CHECK_LAUNCH();
+    return ARF_OK;
+}
+
+extern "C" int arf_stencil_mv_bwd(const float* A, const float* X, const float* gY, float* dA, float* dX, int N, int H,
+                                  int W, int k, int transposed, void* stream) {
+    ARF_REQUIRE(A && X && gY && N > 0 && H > 0 && W > 0 && k >= 0 && k <= 15);
+    if (!dA && !dX) return ARF_OK;
+    long long total = (long long)N * 2 * H * W;
+    stencil_mv_bwd_kernel<<<arf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(A, X, gY, dA, dX, N, H, W, k,
+                                                                                     transposed ? 1 : 0);
+    ARF_CHECK_LAUNCH();
+    return ARF_OK;
+}
+
+extern "C" int arf_trisolve(const float* A, const float* B, const float* C, const float* D, const float* X, float* Y,
+                            long long systems, int M, int N, int upper, void* stream) {
+    ARF_REQUIRE(A && B && C && X && Y && systems > 0 && systems <= 0x7fffffffLL && M > 0 && N > 0);
+    if (M > 1024) return ARF_EUNSUPPORTED;     // thread <-> row
+    const int threads = (M + 31) / 32 * 32;
+    const size_t smem = 2 * (threads + 1) * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (upper) trisolve_kernel<true><<<(int)systems, threads, smem, st>>>(A, B, C, D, X, Y, M, N);
+    else trisolve_kernel<false><<<(int)systems, threads, smem, st>>>(A, B, C, D, X, Y, M, N);
+    ARF_CHECK_LAUNCH();
+    return ARF_OK;
+}
+
+extern "C" int arf_inv_diag(const float* A, const float* B, const float* C, float* Hout, long long systems, int M,
+                            int N, void* stream) {
+    ARF_REQUIRE(A && B && C && Hout && systems > 0 && M > 0 && N > 0);
+    if (M > 1024) return ARF_EUNSUPPORTED;
+    const long long cells = systems * M * N;
+    if (cells > 0x7fffffffLL) return ARF_EUNSUPPORTED;
+    const int threads = (M + 31) / 32 * 32;
+    const size_t smem = 2 * (threads + 1) * sizeof(float);
+    inv_diag_kernel<<<(int)cells, threads, smem, (cudaStream_t)stream>>>(A, B, C, Hout, M, N);
+    ARF_CHECK_LAUNCH();
+    return ARF_OK;
+}

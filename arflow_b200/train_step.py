@@ -23,16 +23,21 @@ class UFlowTrainStep:
         self.use_graph = use_graph
         self.params = [p for p in model.parameters() if p.requires_grad]
         dev = self.params[0].device
-        # flat gradient storage; parameter .grad tensors are views into it
-        total = sum(p.numel() for p in self.params)
-        self.flat_grad = torch.zeros(total, device=dev, dtype=self.params[0].dtype)
-        off = 0
+        # multi-GPU: flat gradient storage, parameter .grad tensors are views into it (16-byte aligned
+        # spans so the accumulation kernels vectorise).  Single GPU: gradients are simply dropped to None
+        # every step, autograd then hands its freshly written tensors over without an accumulate pass.
+        self.flat_grad = None
         self._spans = []
-        for p in self.params:
-            n = p.numel()
-            p.grad = self.flat_grad[off:off + n].view_as(p)
-            self._spans.append((off, off + n))
-            off += n
+        if world_size > 1:
+            off = 0
+            for p in self.params:
+                n = p.numel()
+                self._spans.append((off, off + n))
+                off += (n + 3) // 4 * 4
+            total = off
+            self.flat_grad = torch.zeros(total, device=dev, dtype=self.params[0].dtype)
+            for p, (s0, e0) in zip(self.params, self._spans):
+                p.grad = self.flat_grad[s0:e0].view_as(p)
         self.optimizer = torch.optim.Adam(self.params, lr=lr, betas=betas, eps=eps,
                                           capturable=dev.type == "cuda", fused=dev.type == "cuda")
         # buckets over the flat buffer in REVERSE parameter order (backward produces the decoder's
@@ -43,8 +48,8 @@ class UFlowTrainStep:
             self._comm_stream = torch.cuda.Stream(device=dev)
             bounds = [int(round(total * k / n_buckets)) for k in range(n_buckets + 1)]
             # snap bucket bounds to parameter boundaries
-            ends = [e for (_, e) in self._spans]
-            snapped = [0] + [min(ends, key=lambda e: abs(e - b)) for b in bounds[1:-1]] + [total]
+            starts = [s0 for (s0, _) in self._spans]
+            snapped = [0] + [min(starts, key=lambda s0: abs(s0 - b)) for b in bounds[1:-1]] + [total]
             snapped = sorted(set(snapped))
             self._buckets = [(snapped[i], snapped[i + 1]) for i in range(len(snapped) - 1)]
             self._pending = [0] * len(self._buckets)
@@ -76,9 +81,12 @@ class UFlowTrainStep:
 
     # ---------------------------------------------------------------- the step
     def _step_impl(self, img_pair):
-        self.flat_grad.zero_()
         if self.world_size > 1:
+            self.flat_grad.zero_()
             self._pending = list(self._counts)
+        else:
+            for p in self.params:
+                p.grad = None
         res = self.model(img_pair, with_bk=True)
         flows = [torch.cat([a, b], 1) for a, b in zip(res['flows_fw'], res['flows_bw'])]
         loss, l_ph, l_sm, flow_mean, _ = self.loss_fn(flows, img_pair)

@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (default: the named config)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="pairs per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--channels-last", action="store_true", help="experiment: NHWC conv activations")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run ONE eager step between cudaProfilerStart/Stop (for `ncu --profile-from-start off`) and exit")
     return ap.parse_args()
 
 
@@ -187,6 +190,8 @@ def main_b200(args):
     model = PWCFlow(types.SimpleNamespace(level_dropout=0.1, feature_norm=True)).to(dev)
     model.init_weights()
     model.train()
+    if args.channels_last:
+        model = model.to(memory_format=torch.channels_last)
     loss_fn = UFlowLoss(types.SimpleNamespace(edge_constant=150, w_smooth=4.0, w_census=1.0, with_bk=True,
                                                smooth_order=1))
     step = UFlowTrainStep(model, loss_fn, lr=1e-4, use_graph=not args.no_graph, world_size=world)
@@ -200,6 +205,18 @@ def main_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.profile_step:
+        eager = UFlowTrainStep(model, loss_fn, lr=1e-4, use_graph=False, world_size=1)
+        for i in range(3):
+            eager(devb[i % n_host])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        eager(devb[3])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiled": "one eager train step", "launches": None}), flush=True)
+        return
 
     # ---- warm-up (also captures the graph) ----
     for i in range(max(args.warmup, 3)):
@@ -283,7 +300,7 @@ def main_b200(args):
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": gb, "per_gpu_batch": B, "height": H, "width": W,
-                           "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph,
+                           "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph, "channels_last": args.channels_last,
                            "conv_math": "cuDNN fp32 tensors, torch default allow_tf32=%s" % torch.backends.cudnn.allow_tf32,
                            "l2": "per-step working set (activations) is several GB >> 126 MB L2; 4 input batches rotate",
                            "loss_last_step": last},

@@ -157,6 +157,29 @@ int arf_smooth_bwd(const float* img, const float* flow, const float* gloss, floa
                    int order, int wstride, int woff, int penalty, float edge, float eps2, float final_scale,
                    void* stream);
 
+/* ---------------------------------------------------------------- stencil-triangular ---- */
+/* matrix_vector_product_general / _T_general (utils/triag_solve.py:29-43, 59-73).
+ * A: (N, 2*(k+1)^2, H, W), tap t = i*(k+1)+j occupies channels 2t, 2t+1 (u, v); X, Y: (N,2,H,W).
+ *   transposed=0:  Y[p] = sum_t A[t][p-(i,j)] * X[p-(i,j)]      (y = L x, taps leaving the image dropped)
+ *   transposed=1:  Y[p] = sum_t A[t][p] * X[p+(i,j)]            (y = L^T x) */
+int arf_stencil_mv_fwd(const float* A, const float* X, float* Y, int N, int H, int W, int k, int transposed,
+                       void* stream);
+/* dA (same shape as A) and dX (same shape as X) of the product above; either may be NULL. */
+int arf_stencil_mv_bwd(const float* A, const float* X, const float* gY, float* dA, float* dX, int N, int H, int W,
+                       int k, int transposed, void* stream);
+
+/* forward_substitution (upper=0) / backward_substitution (upper=1) of triag_solve_cuda
+ * (utils/triag_solve/triag_solve.cpp:12-36, triag_solve_cuda.cu:7-69; Python twins triag_solve.py:76-115).
+ * A: (S,M,N) diagonal, B: (S,M,N-1) left/right, C: (S,M-1,N) above/below, D: (S,M-1,N-1) diagonal neighbour
+ * (may be NULL), X -> Y: (S,M,N); S = batch*channels systems.  Y may not alias X. M <= 1024. */
+int arf_trisolve(const float* A, const float* B, const float* C, const float* D, const float* X, float* Y,
+                 long long systems, int M, int N, int upper, void* stream);
+
+/* inverse_diagonal (triag_solve.cpp:38-45, triag_solve_cuda.cu:72-139): H[s,k,l] = || L^-1 e_(k,l) ||^2,
+ * L built from A, B, C only. */
+int arf_inv_diag(const float* A, const float* B, const float* C, float* H, long long systems, int M, int N,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -393,3 +393,61 @@ class CpuTrainStep:
         out[0].backward()
         self.opt.step()
         return float(out[0].detach())
+
+
+# --------------------------------------------------------------------------- triangular -----
+def stencil_mv(A, X, k=1, transposed=False):
+    """matrix_vector_product_general / _T_general (triag_solve.py:29-43, 59-73): tap (i,j) of channel ch
+    lives in A[:, 2*(i*(k+1)+j)+ch]; L x accumulates A*X of the source pixel into the pixel (i,j) further
+    down/right, L^T x reads X from there."""
+    H, W = X.shape[2:]
+    Y = torch.zeros_like(X)
+    for i in range(k + 1):
+        for j in range(k + 1):
+            t = 2 * (i * (k + 1) + j)
+            a = A[:, t:t + 2, :H - i, :W - j]
+            if transposed:
+                Y[:, :, :H - i, :W - j] = Y[:, :, :H - i, :W - j] + a * X[:, :, i:, j:]
+            else:
+                Y[:, :, i:, j:] = Y[:, :, i:, j:] + a * X[:, :, :H - i, :W - j]
+    return Y
+
+
+def substitution(A, B, C, D, X, upper=False):
+    """forward_substitution / backward_substitution (triag_solve.py:76-115; triag_solve_cuda.cu:7-69),
+    vectorised over the (batch, channel) systems, float64 numpy."""
+    a, b, c, x = (t.detach().double().numpy() for t in (A, B, C, X))
+    d = D.detach().double().numpy() if D is not None else None
+    M, N = a.shape[2:]
+    y = x.copy()
+    rows = range(M - 1, -1, -1) if upper else range(M)
+    cols = range(N - 1, -1, -1) if upper else range(N)
+    s = 1 if upper else -1          # neighbour direction
+    for i in rows:
+        for j in cols:
+            ii, jj = i + s, j + s
+            hi, hj = 0 <= ii < M, 0 <= jj < N
+            ci, cj = (i, j) if upper else (i - 1, j - 1)   # coefficient position
+            v = y[:, :, i, j]
+            if hi:
+                v = v - y[:, :, ii, j] * c[:, :, ci, j]
+            if hj:
+                v = v - y[:, :, i, jj] * b[:, :, i, cj]
+            if hi and hj and d is not None:
+                v = v - y[:, :, ii, jj] * d[:, :, ci, cj]
+            y[:, :, i, j] = v / a[:, :, i, j]
+    return torch.from_numpy(y)
+
+
+def inverse_diagonal(A, B, C):
+    """inverse_diagonal (triag_solve_cuda.cu:72-139) == marginal_variances (triag_solve.py:205-218):
+    squared norm of every column of L^-1, one unit-vector solve per pixel."""
+    M, N = A.shape[2:]
+    Hh = torch.zeros_like(A, dtype=torch.float64)
+    for i in range(M):
+        for j in range(N):
+            e = torch.zeros_like(A, dtype=torch.float64)
+            e[:, :, i, j] = 1
+            y = substitution(A, B, C, None, e)
+            Hh[:, :, i, j] = (y * y).sum(dim=(2, 3))
+    return Hh

