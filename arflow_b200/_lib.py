@@ -42,6 +42,10 @@ PROTOTYPES = {
     "arf_stencil_mv_bwd": [_P] * 5 + [c_int] * 5 + [_P],
     "arf_trisolve": [_P] * 6 + [ctypes.c_longlong, c_int, c_int, c_int, _P],
     "arf_inv_diag": [_P] * 4 + [ctypes.c_longlong, c_int, c_int, _P],
+    "arf_ssim_fwd": [_P] * 4 + [ctypes.c_longlong] + [c_int] * 5 + [_P],
+    "arf_ssim_bwd": [_P] * 7 + [ctypes.c_longlong] + [c_int] * 5 + [_P],
+    "arf_resampler_fwd": [_P, _P, _P, ctypes.c_longlong, _P] + [c_int] * 4 + [ctypes.c_longlong, _P],
+    "arf_resampler_bwd": [_P, _P, _P, ctypes.c_longlong, _P, _P, _P, _P, ctypes.c_longlong] + [c_int] * 4 + [ctypes.c_longlong, _P],
 }
 _RESTYPES = {"arf_error_string": ctypes.c_char_p, "arf_launch_count": ctypes.c_longlong}
 

@@ -83,3 +83,9 @@ def smooth_grad_1st(flo, image, alpha, penalty="abs"):
 def smooth_grad_2nd(flo, image, alpha):
     """loss_blocks.py:112-124."""
     return _SmoothFunction.apply(flo, image, 2, 1, 1, 1, alpha, 0.0, 0.5)
+
+
+def SSIM(x, y, md=1):
+    """loss_blocks.py:65-84 — valid (unpadded) box filters, output (B,C,H-2md,W-2md)."""
+    from .uflow_utils import _SsimFunction
+    return _SsimFunction.apply(x, y, 2 * md + 1, True, 1)

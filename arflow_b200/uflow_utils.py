@@ -234,3 +234,50 @@ def census_loss_no_penalty(image_a, image_b, mask, patch_size=7):
     hamming = _CensusHammingFunction.apply(image_a, image_b, patch_size, 1.0)
     padded_mask = zero_mask_border(mask, patch_size)
     return hamming, padded_mask / (torch.sum(padded_mask.detach()) + 1e-6)
+
+
+# --------------------------------------------------------------------------- SSIM ----------
+class _SsimFunction(torch.autograd.Function):
+    """Five box filters + the SSIM ratios in one pass (csrc/ssim.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, y, patch, valid, mode):
+        x, y = x.contiguous(), y.contiguous()
+        if x.shape != y.shape or x.dim() != 4:
+            raise ValueError("SSIM: expected two (B,C,H,W) tensors of equal shape")
+        B, C, H, W = x.shape
+        r = patch // 2
+        Ho, Wo = (H - 2 * r, W - 2 * r) if valid else (H, W)
+        with torch.cuda.device_of(x):
+            o1 = _new_like(x, (B, C, Ho, Wo))
+            o2 = _new_like(x, (B, C, Ho, Wo)) if mode == 0 else None
+            _lib.call("arf_ssim_fwd", _lib.dev_ptr(x, "x"), _lib.dev_ptr(y, "y"), _lib.dev_ptr(o1),
+                      _lib.dev_ptr(o2, allow_none=True), B * C, H, W, patch, int(valid), mode, _lib.stream_ptr())
+        ctx.save_for_backward(x, y)
+        ctx.cfg = (patch, int(valid), mode, Ho, Wo)
+        if mode == 0:
+            return o1, o2
+        return o1
+
+    @staticmethod
+    def backward(ctx, g1, g2=None):
+        x, y = ctx.saved_tensors
+        patch, valid, mode, Ho, Wo = ctx.cfg
+        B, C, H, W = x.shape
+        g1 = g1.contiguous()
+        g2 = g2.contiguous() if g2 is not None else None
+        with torch.cuda.device_of(x):
+            coef = _new_like(x, (5, B * C, Ho, Wo))
+            gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+            gy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+            _lib.call("arf_ssim_bwd", _lib.dev_ptr(x), _lib.dev_ptr(y), _lib.dev_ptr(g1, "grad"),
+                      _lib.dev_ptr(g2, allow_none=True), _lib.dev_ptr(coef), _lib.dev_ptr(gx, allow_none=True),
+                      _lib.dev_ptr(gy, allow_none=True), B * C, H, W, patch, valid, mode, _lib.stream_ptr())
+        return gx, gy, None, None, None
+
+
+def ssim_loss(image_a, image_b, mask, patch_size=7):
+    """uflow_utils.py:309-334 -> ([d1_sq, d2_sq], weight)."""
+    d1_sq, d2_sq = _SsimFunction.apply(image_a, image_b, patch_size, False, 0)
+    padded_mask = zero_mask_border(mask, patch_size=patch_size)
+    return [d1_sq, d2_sq], padded_mask / (torch.sum(padded_mask.detach()) + 1e-6)

@@ -180,6 +180,28 @@ int arf_trisolve(const float* A, const float* B, const float* C, const float* D,
 int arf_inv_diag(const float* A, const float* B, const float* C, float* H, long long systems, int M, int N,
                  void* stream);
 
+/* ---------------------------------------------------------------- SSIM ------------------ */
+/* x, y: (planes,H,W).  valid=0: zero-padded P x P box filters with divisor P*P, output (planes,H,W)
+ * (ssim_loss, uflow_utils.py:309-334); valid=1: unpadded filters, output (planes,H-P+1,W-P+1)
+ * (SSIM, loss_blocks.py:65-84).  mode 0: out1 = clamp(1-S1,0,1), out2 = clamp(1-S2,0,1);
+ * mode 1: out1 = clamp((1 - S1*S2)/2, 0, 1), out2 unused.  patch in {3,5,7}. */
+int arf_ssim_fwd(const float* x, const float* y, float* out1, float* out2, long long planes, int H, int W,
+                 int patch, int valid, int mode, void* stream);
+/* g1, g2: upstream gradients of out1, out2; coef: workspace of 5*planes*Ho*Wo floats; gx, gy may be NULL. */
+int arf_ssim_bwd(const float* x, const float* y, const float* g1, const float* g2, float* coef, float* gx,
+                 float* gy, long long planes, int H, int W, int patch, int valid, int mode, void* stream);
+
+/* ---------------------------------------------------------------- NHWC resampler -------- */
+/* resampler_with_unstacked_warp(data, warp_x, warp_y, safe=True) (utils/uflow_resampler.py:155-241).
+ * data: (B,H,W,C); warp_x/warp_y: B*P coordinates read with element stride wstride (2 for the interleaved
+ * (...,2) tensor of `resampler`, :137-152); out: (B,P,C).  Taps floor/ceil, out-of-range taps contribute 0. */
+int arf_resampler_fwd(const float* data, const float* warp_x, const float* warp_y, long long wstride, float* out,
+                      int B, int H, int W, int C, long long P, void* stream);
+/* gdata (zero-filled here, atomics), gwx/gwy written with element stride gwstride; each may be NULL. */
+int arf_resampler_bwd(const float* data, const float* warp_x, const float* warp_y, long long wstride,
+                      const float* gout, float* gdata, float* gwx, float* gwy, long long gwstride,
+                      int B, int H, int W, int C, long long P, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -451,3 +451,58 @@ def inverse_diagonal(A, B, C):
             y = substitution(A, B, C, None, e)
             Hh[:, :, i, j] = (y * y).sum(dim=(2, 3))
     return Hh
+
+
+# --------------------------------------------------------------------------- SSIM / resampler
+def _box(t, patch, valid):
+    """AvgPool2d(patch, 1, 0 | patch//2) with zeros counted (count_include_pad): sum of shifted slices / patch^2."""
+    r = patch // 2
+    if not valid:
+        t = F.pad(t, [r] * 4)
+    H, W = t.shape[2] - 2 * r, t.shape[3] - 2 * r
+    acc = 0
+    for dy in range(patch):
+        for dx in range(patch):
+            acc = acc + t[:, :, dy:dy + H, dx:dx + W]
+    return acc / (patch * patch)
+
+
+def _ssim_terms(x, y, patch, valid):
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    mx, my = _box(x, patch, valid), _box(y, patch, valid)
+    sx = _box(x * x, patch, valid) - mx * mx
+    sy = _box(y * y, patch, valid) - my * my
+    sxy = _box(x * y, patch, valid) - mx * my
+    return (2 * mx * my + C1) / (mx * mx + my * my + C1), (2 * sxy + C2) / (sx + sy + C2)
+
+
+def ssim_loss(image_a, image_b, mask, patch=7):
+    """uflow_utils.py:309-334."""
+    S1, S2 = _ssim_terms(image_a, image_b, patch, False)
+    pm = zero_border(mask, patch // 2)
+    return [(1 - S1).clamp(0, 1), (1 - S2).clamp(0, 1)], pm / (pm.detach().sum() + 1e-6)
+
+
+def ssim_valid(x, y, md=1):
+    """SSIM of loss_blocks.py:65-84."""
+    S1, S2 = _ssim_terms(x, y, 2 * md + 1, True)
+    return ((1 - S1 * S2) / 2).clamp(0, 1)
+
+
+def resampler(data, warp_x, warp_y):
+    """resampler_with_unstacked_warp (uflow_resampler.py:155-241): NHWC data, floor/ceil taps, zero outside."""
+    B, H, W, C = data.shape
+    shape = warp_x.shape
+    wx, wy = warp_x.reshape(B, -1), warp_y.reshape(B, -1)
+    x0, y0 = torch.floor(wx), torch.floor(wy)
+    fx, fy = (wx - x0).unsqueeze(-1), (wy - y0).unsqueeze(-1)
+    x1, y1 = torch.ceil(wx), torch.ceil(wy)
+    flat = data.reshape(B, H * W, C)
+
+    def tap(yy, xx):
+        ok = ((xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)).unsqueeze(-1).to(data.dtype)
+        lin = (yy.clamp(0, H - 1) * W + xx.clamp(0, W - 1)).long().unsqueeze(-1).expand(B, -1, C)
+        return flat.gather(1, lin) * ok
+
+    out = (tap(y0, x0) * (1 - fx) + tap(y0, x1) * fx) * (1 - fy) + (tap(y1, x0) * (1 - fx) + tap(y1, x1) * fx) * fy
+    return out.reshape(*shape, C)

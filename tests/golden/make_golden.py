@@ -8,6 +8,7 @@ Each fixture holds seeded float32 inputs and the reference's outputs computed tw
 ("truth", suffix _f64) and in float32 (reference precision, suffix _f32).  tests/ never imports the
 reference; they read these files.
 """
+import json
 import os
 import sys
 import types
@@ -160,6 +161,53 @@ def main():
         cfg = EasyDict(edge_constant=150, w_smooth=4.0, w_census=1.0, with_bk=True, smooth_order=order)
         res = both(lambda o0, o1, o2, t: UFlowLoss(cfg)([o0, o1, o2], t), out0, out1, out2, target, grads=(0, 2))
         save("uflow_loss_order%d" % order, (out0, out1, out2, target), res)
+
+    # ---- SSIM blocks and the NHWC resampler ----
+    from utils import uflow_resampler as ur
+    a, b = rnd(gen, 2, 3, 14, 18, uniform=True), rnd(gen, 2, 3, 14, 18, uniform=True)
+    mask = rnd(gen, 2, 1, 14, 18, uniform=True)
+    res = {}
+    for kk, v in both(lambda x, y, m: tuple(uu.ssim_loss(x, y, m)[0]) + (uu.ssim_loss(x, y, m)[1],), a, b, mask,
+                      grads=(0, 1)).items(): res["ssimloss_" + kk] = v
+    for kk, v in both(lambda x, y: lb.SSIM(x, y, md=1), a, b, grads=(0, 1)).items(): res["ssim1_" + kk] = v
+    for kk, v in both(lambda x, y: lb.SSIM(x, y, md=2), a, b).items(): res["ssim2_" + kk] = v
+    data = rnd(gen, 2, 6, 7, 5)
+    wxy = torch.stack([rnd(gen, 2, 4, 9, uniform=True) * 8 - 1, rnd(gen, 2, 4, 9, uniform=True) * 7 - 1], -1)
+    wxy[0, 0, 0] = torch.tensor([2.0, 3.0])      # exact integer coordinates: floor == ceil
+    for kk, v in both(lambda d, w: ur.resampler(d, w), data, wxy, grads=(0, 1)).items(): res["resampler_" + kk] = v
+    res["data"], res["warp"] = data.numpy(), wxy.numpy()
+    save("ssim_resampler", (a, b, mask), res)
+
+    # ---- UFlowElboLoss (noise injected so the fixture is reproducible) ----
+    from losses.uflow_elbo_loss import UFlowElboLoss
+    He, We, Be = 32, 40, 2
+    base = dict(edge_constant=150, edge_asymp=0.01, w_smooth=4.0, penalty_smooth="charbonnier", data_loss=["census"],
+                data_weight=[1.0], data_penalty=["abs_robust_loss"], w_entropy=0.1, with_bk=True, n_components=1,
+                inv_cov=False, approx_entropy=False, natural_grad=False, isotropic_smooth=False)
+    cases = {
+        "elbo_sparse": dict(base, approx="sparse", cov_supp=3, n_samples=2, occ_type="sample", closed_form_smooth=False,
+                            w_oof=0.0, w_occ=0.0, offdiag_reg=0.01),
+        "elbo_diag": dict(base, approx="diag", cov_supp=0, n_samples=1, occ_type="mean", closed_form_smooth=True,
+                          order_smooth=1, w_oof=0.5, w_occ=0.3, offdiag_reg=0.0),
+    }
+    for name, c in cases.items():
+        cfg = EasyDict(c)
+        nch = 4 if c["approx"] == "diag" else 4 + 2 * ((c["cov_supp"] + 1) ** 2 - 1)
+        fw2 = rnd(gen, Be, nch, He // 4, We // 4, scale=0.5)
+        bw2 = rnd(gen, Be, nch, He // 4, We // 4, scale=0.5)
+        im1, im2 = rnd(gen, Be, 3, He, We, uniform=True), rnd(gen, Be, 3, He, We, uniform=True)
+        eps = [rnd(gen, c["n_samples"] * Be, 2, He // 4, We // 4) for _ in range(2)]
+
+        def run(f, b, i1, i2):
+            loss = UFlowElboLoss(cfg)
+            it = iter(eps)
+            loss.Normal.sample = lambda size: next(it).to(f.dtype)
+            out = loss({"flows_fw": [None, None, f], "flows_bw": [None, None, b]}, i1, i2)
+            return out[:5] if not isinstance(out[4], (int, float)) else out[:4] + (torch.zeros((), dtype=f.dtype),)
+        res = both(run, fw2, bw2, im1, im2, grads=(0, 1))
+        res["eps0"], res["eps1"] = eps[0].numpy(), eps[1].numpy()
+        res["cfg"] = np.asarray(json.dumps(c))
+        save(name, (fw2, bw2, im1, im2), res)
 
     # ---- stencil-triangular algebra ----
     from utils import triag_solve as ts

@@ -123,3 +123,56 @@ def test_uflow_loss_full_size_vs_oracle(oracle):
         assert_close(out[k], ref[k], RTOL_VALUE, "output %d" % k)
     assert_close(a0.grad, r0.grad, RTOL_GRAD)
     assert_close(a2.grad, r2.grad, RTOL_GRAD)
+
+
+def test_ssim_and_resampler_golden():
+    from arflow_b200 import loss_blocks as lb
+    from arflow_b200 import uflow_resampler as ur
+    from arflow_b200 import uflow_utils as uu
+    g = load_golden("ssim_resampler")
+    a, b, m = g["in0"], g["in1"], g["in2"]
+    outs, (ga, gb) = _grads(lambda x, y, mm: tuple(uu.ssim_loss(x, y, mm)[0]) + (uu.ssim_loss(x, y, mm)[1],),
+                            [a, b, m], (0, 1))
+    for k in range(3):
+        assert_close(outs[k], g["ssimloss_out%d_f64" % k], RTOL_VALUE, "ssim_loss out %d" % k)
+    assert_close(ga, g["ssimloss_grad0_f64"], RTOL_GRAD)
+    assert_close(gb, g["ssimloss_grad1_f64"], RTOL_GRAD)
+    (o,), (ga, gb) = _grads(lambda x, y: lb.SSIM(x, y, md=1), [a, b], (0, 1))
+    assert_close(o, g["ssim1_out0_f64"], RTOL_VALUE)
+    assert_close(ga, g["ssim1_grad0_f64"], RTOL_GRAD)
+    assert_close(gb, g["ssim1_grad1_f64"], RTOL_GRAD)
+    assert_close(lb.SSIM(a.cuda(), b.cuda(), md=2), g["ssim2_out0_f64"], RTOL_VALUE)
+    (o,), (gd, gw) = _grads(lambda d, w: ur.resampler(d, w), [g["data"], g["warp"]], (0, 1))
+    assert_close(o, g["resampler_out0_f64"], RTOL_VALUE)
+    assert_close(gd, g["resampler_grad0_f64"], RTOL_GRAD)
+    assert_close(gw, g["resampler_grad1_f64"], RTOL_GRAD)
+
+
+@pytest.mark.parametrize("name", ["elbo_sparse", "elbo_diag"])
+def test_uflow_elbo_loss_golden(name):
+    """UFlowElboLoss (non-diagonal stencil covariance, and diagonal with closed-form smoothness, out-of-frame
+    and occlusion penalties) against the reference run with the same injected noise."""
+    import json
+    import numpy as np
+    import os
+    from conftest import GOLDEN
+    from arflow_b200.uflow_elbo_loss import UFlowElboLoss
+    g = load_golden(name) if False else None
+    with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
+        cfg = types.SimpleNamespace(**json.loads(str(z["cfg"])))
+        t = {k: torch.from_numpy(z[k]) for k in z.files if k != "cfg"}
+    eps = [t["eps0"].cuda(), t["eps1"].cuda()]
+
+    def run(f, b, i1, i2):
+        loss = UFlowElboLoss(cfg)
+        it = iter(eps)
+        loss._normal = lambda size, like: next(it)
+        out = loss({"flows_fw": [None, None, f], "flows_bw": [None, None, b]}, i1, i2)
+        o4 = out[4] if torch.is_tensor(out[4]) else torch.zeros((), device=f.device)
+        return out[:4] + (o4,)
+
+    outs, (gf, gb) = _grads(run, [t["in0"], t["in1"], t["in2"], t["in3"]], (0, 1))
+    for k in range(5):
+        assert_close(outs[k], t["out%d_f32" % k], 2e-5, "%s output %d" % (name, k))
+    assert_close(gf, t["grad0_f32"], RTOL_GRAD, "d/d flows_fw[2]")
+    assert_close(gb, t["grad1_f32"], RTOL_GRAD, "d/d flows_bw[2]")

@@ -169,3 +169,22 @@ def test_triangular(oracle):
         from_taps[:, 6 + ch, :-1, :-1] = d[:, ch]
     assert_close(oracle.stencil_mv(from_taps, y, 1), x.double(), 1e-10)
     assert_close(oracle.stencil_mv(from_taps, y, 1), g["mv4_out0_f64"] * 0 + x.double(), 1e-10)
+
+
+def test_ssim_and_resampler(oracle):
+    g = load_golden("ssim_resampler")
+    a, b, m = g["in0"], g["in1"], g["in2"]
+    outs, (ga, gb) = _grads(lambda x, y, mm: tuple(oracle.ssim_loss(x, y, mm)[0]) + (oracle.ssim_loss(x, y, mm)[1],),
+                            [a, b, m], (0, 1))
+    for k in range(3):
+        assert_close(outs[k], g["ssimloss_out%d_f64" % k], TIGHT)
+    assert_close(ga, g["ssimloss_grad0_f64"], 1e-10)
+    assert_close(gb, g["ssimloss_grad1_f64"], 1e-10)
+    (o,), (ga, gb) = _grads(lambda x, y: oracle.ssim_valid(x, y, 1), [a, b], (0, 1))
+    assert_close(o, g["ssim1_out0_f64"], TIGHT)
+    assert_close(ga, g["ssim1_grad0_f64"], 1e-10)
+    assert_close(oracle.ssim_valid(a.double(), b.double(), 2), g["ssim2_out0_f64"], TIGHT)
+    (o,), (gd, gw) = _grads(lambda d, w: oracle.resampler(d, w[..., 0], w[..., 1]), [g["data"], g["warp"]], (0, 1))
+    assert_close(o, g["resampler_out0_f64"], TIGHT)
+    assert_close(gd, g["resampler_grad0_f64"], TIGHT)
+    assert_close(gw, g["resampler_grad1_f64"], 1e-10)
