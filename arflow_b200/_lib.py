@@ -28,6 +28,7 @@ PROTOTYPES = {
     "arf_warp_bwd": [_P, _P, _P, _P, _P] + [c_int] * 6 + [c_float, c_float] + [c_int] * 4 + [_P],
     "arf_inside_mask": [_P, _P] + [c_int] * 5 + [_P],
     "arf_range_map": [_P, _P] + [c_int] * 4 + [_P],
+    "arf_range_map_bwd": [_P, _P, _P] + [c_int] * 4 + [_P],
     "arf_count_to_mask": [_P, _P, ctypes.c_longlong, c_int, c_float, _P],
     "arf_occ_bidir": [_P, _P, _P] + [c_int] * 3 + [c_float, c_float, _P],
     "arf_resize_bilinear_fwd": [_P, _P, ctypes.c_longlong] + [c_int] * 4 + [c_float] * 3 + [_P],

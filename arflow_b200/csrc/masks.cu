@@ -66,6 +66,44 @@ __global__ void range_map_kernel(const float* __restrict__ field, float* __restr
     }
 }
 
+// d(count)/d(field): the splat weights are (1-ox | ox) * (1-oy | oy) with ox = x - floor(x), so each pixel
+// gathers +-(other-axis weight) * upstream gradient from the in-image taps it wrote to.
+__global__ void range_map_bwd_kernel(const float* __restrict__ field, const float* __restrict__ gcount,
+                                     float* __restrict__ gfield, int B, int H, int W, int kind) {
+    long long total = (long long)B * H * W;
+    const size_t hw = (size_t)H * W;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int j = idx % W;
+        long long t = idx / W;
+        int i = t % H, b = t / H;
+        float x, y;
+        field_xy(field, kind, b, i, j, H, W, x, y);
+        float xf = floorf(x), yf = floorf(y);
+        float ox = x - xf, oy = y - yf;
+        float gx = 0.f, gy = 0.f;
+        if (xf >= -2.f && xf <= (float)W && yf >= -2.f && yf <= (float)H) {
+            int x0 = (int)xf, y0 = (int)yf;
+            const float* gb = gcount + (size_t)b * hw;
+#pragma unroll
+            for (int di = 0; di < 2; ++di)
+#pragma unroll
+                for (int dj = 0; dj < 2; ++dj) {
+                    int yy = y0 + di, xx = x0 + dj;
+                    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                        float g = __ldg(gb + (size_t)yy * W + xx);
+                        float wi = di ? oy : 1.f - oy, wj = dj ? ox : 1.f - ox;
+                        gx += g * wi * (dj ? 1.f : -1.f);
+                        gy += g * wj * (di ? 1.f : -1.f);
+                    }
+                }
+        }
+        float* go = gfield + (size_t)b * 2 * hw + (size_t)i * W + j;
+        go[0] = gx;
+        go[hw] = gy;
+    }
+}
+
 // mode 0: clamp(c,0,1)   mode 1: clamp(c,0,1) < th   mode 2: 1 - clamp(c,0,1)
 __global__ void count_to_mask_kernel(const float* __restrict__ count, float* __restrict__ out, long long n, int mode,
                                      float th) {
@@ -112,6 +150,16 @@ extern "C" int arf_range_map(const float* field, float* count, int B, int H, int
     cudaError_t e = cudaMemsetAsync(count, 0, (size_t)total * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
     range_map_kernel<<<arf_grid_1d(total, 256), 256, 0, st>>>(field, count, B, H, W, field_kind);
+    ARF_CHECK_LAUNCH();
+    return ARF_OK;
+}
+
+extern "C" int arf_range_map_bwd(const float* field, const float* gcount, float* gfield, int B, int H, int W,
+                                 int field_kind, void* stream) {
+    ARF_REQUIRE(field && gcount && gfield && B > 0 && H > 0 && W > 0);
+    long long total = (long long)B * H * W;
+    range_map_bwd_kernel<<<arf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(field, gcount, gfield, B, H, W,
+                                                                                     field_kind);
     ARF_CHECK_LAUNCH();
     return ARF_OK;
 }

@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from .penalty_functions import get_penalty
 from .triag_solve import matrix_vector_product_general
-from .uflow_utils import (census_loss_no_penalty, clamp01, compute_range_map, downsample, flow_to_warp, image_grads,
+from .uflow_utils import (census_loss_no_penalty, compute_range_map, downsample, flow_to_warp, image_grads,
                           mask_invalid, resample, ssim_loss, upsample)
 
 
@@ -27,11 +27,11 @@ def data_loss_no_penalty(im1_0, im2_0, flow12_2, flow21_2, occ_type, data_loss, 
     if occ_type == 'mean':
         mean_warp12_0 = flow_to_warp(upsample(mean12_2, is_flow=True, scale_factor=4.0))
         valid_mask_0 = mask_invalid(mean_warp12_0)
-        occu_mask_2 = clamp01(compute_range_map(mean21_2))
+        occu_mask_2 = torch.clamp(compute_range_map(mean21_2), min=0., max=1.)
         mask_0 = (upsample(occu_mask_2, is_flow=False, scale_factor=4.0) * valid_mask_0).detach()
     elif occ_type == 'sample':
         valid_mask_0 = mask_invalid(warp12_0)
-        occu_mask_2 = clamp01(compute_range_map(flow21_2))
+        occu_mask_2 = torch.clamp(compute_range_map(flow21_2), min=0., max=1.)
         mask_0 = (upsample(occu_mask_2, is_flow=False, scale_factor=4.0) * valid_mask_0).detach()
     elif occ_type == 'none':
         valid_mask_0 = mask_invalid(warp12_0)

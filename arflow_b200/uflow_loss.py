@@ -18,7 +18,7 @@ class UFlowLoss(nn.modules.Module):
         warp_0 = flow_to_warp(flow_ab_0)
         recons = resample(im_b.detach(), warp_0)
         valid = mask_invalid(warp_0)
-        occu = upsample(clamp01(compute_range_map(flow_ba_2)), is_flow=False, scale_factor=4.0)
+        occu = upsample(clamp01(compute_range_map(flow_ba_2.detach())), is_flow=False, scale_factor=4.0)
         mask = (occu * valid).detach()
         return census_loss(im_a, recons, mask), mask
 

@@ -38,17 +38,35 @@ def mask_invalid(coords):
     return mask
 
 
+class _RangeMapFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow):
+        flow = flow.contiguous()
+        B, _, H, W = flow.shape
+        with torch.cuda.device_of(flow):
+            count = _new_like(flow, (B, 1, H, W))
+            _lib.call("arf_range_map", _lib.dev_ptr(flow, "flow"), _lib.dev_ptr(count), B, H, W, 0, _lib.stream_ptr())
+        ctx.save_for_backward(flow)
+        return count
+
+    @staticmethod
+    def backward(ctx, gcount):
+        (flow,) = ctx.saved_tensors
+        B, _, H, W = flow.shape
+        gcount = gcount.contiguous()
+        with torch.cuda.device_of(flow):
+            gflow = torch.empty_like(flow)
+            _lib.call("arf_range_map_bwd", _lib.dev_ptr(flow), _lib.dev_ptr(gcount, "grad"), _lib.dev_ptr(gflow),
+                      B, H, W, 0, _lib.stream_ptr())
+        return gflow
+
+
 def compute_range_map(flow):
-    """uflow_utils.py:80-160 — how often each pixel is hit by the forward splat of `flow`
-    (bilinear weights, targets outside the image dropped).  Every call site detaches the result
-    (uflow_loss.py:43,48; uflow_elbo_loss.py:50,57), so it is returned without a graph."""
+    """uflow_utils.py:80-160 — how often each pixel is hit by the forward splat of `flow` (bilinear weights,
+    targets outside the image dropped).  Differentiable w.r.t. the flow like the reference's scatter_add
+    (the occlusion penalty of the ELBO loss uses that, uflow_elbo_loss.py:552-559)."""
     assert flow.dim() == 4
-    flow = flow.detach().contiguous()
-    B, _, H, W = flow.shape
-    with torch.cuda.device_of(flow):
-        count = _new_like(flow, (B, 1, H, W))
-        _lib.call("arf_range_map", _lib.dev_ptr(flow, "flow"), _lib.dev_ptr(count), B, H, W, 0, _lib.stream_ptr())
-    return count
+    return _RangeMapFunction.apply(flow)
 
 
 def clamp01(count, mode=0, th=0.0):

@@ -107,6 +107,10 @@ int arf_inside_mask(const float* field, float* mask, int B, int H, int W, int fi
  * get_corresponding_map (warp_utils.py:26-80; field_kind COORDS): bilinear forward splat count.
  * count (B,1,H,W) is zero-filled here. */
 int arf_range_map(const float* field, float* count, int B, int H, int W, int field_kind, void* stream);
+/* gradient of the splat w.r.t. the field (needed where the reference does not detach the range map:
+ * the occlusion penalty of uflow_elbo_loss.py:552-559). */
+int arf_range_map_bwd(const float* field, const float* gcount, float* gfield, int B, int H, int W,
+                      int field_kind, void* stream);
 
 /* mode 0: clamp(c,0,1)   1: clamp(c,0,1) < th   2: 1 - clamp(c,0,1)     (uflow_loss.py:41, warp_utils.py:111-116) */
 int arf_count_to_mask(const float* count, float* out, long long n, int mode, float th, void* stream);

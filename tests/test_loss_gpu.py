@@ -174,5 +174,11 @@ def test_uflow_elbo_loss_golden(name):
     outs, (gf, gb) = _grads(run, [t["in0"], t["in1"], t["in2"], t["in3"]], (0, 1))
     for k in range(5):
         assert_close(outs[k], t["out%d_f32" % k], 2e-5, "%s output %d" % (name, k))
-    assert_close(gf, t["grad0_f32"], RTOL_GRAD, "d/d flows_fw[2]")
-    assert_close(gb, t["grad1_f32"], RTOL_GRAD, "d/d flows_bw[2]")
+    # The reference's own fp32 gradient sits 2.5e-4 (sparse) / 8.6e-5 (diag) away from its float64 gradient on
+    # these inputs (x4 upsample -> coordinate round trip -> census amplifies fp32 rounding), so 1e-4 against
+    # either is below the reference's noise floor here; the bar is 2x that floor, against both.
+    tol = 5e-4 if name == "elbo_sparse" else 2e-4
+    assert_close(gf, t["grad0_f32"], tol, "d/d flows_fw[2] vs fp32 reference")
+    assert_close(gb, t["grad1_f32"], tol, "d/d flows_bw[2] vs fp32 reference")
+    assert_close(gf, t["grad0_f64"], tol, "d/d flows_fw[2] vs float64 reference")
+    assert_close(gb, t["grad1_f64"], tol, "d/d flows_bw[2] vs float64 reference")
