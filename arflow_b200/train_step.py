@@ -40,33 +40,43 @@ class UFlowTrainStep:
                 p.grad = self.flat_grad[s0:e0].view_as(p)
         self.optimizer = torch.optim.Adam(self.params, lr=lr, betas=betas, eps=eps,
                                           capturable=dev.type == "cuda", fused=dev.type == "cuda")
-        # buckets over the flat buffer in REVERSE parameter order (backward produces the decoder's
-        # gradients first, the feature pyramid's last)
+        # buckets over the flat buffer; a bucket is all-reduced (on a side stream, overlapping the rest of
+        # backward) as soon as the last of its gradients has been written.  Parameters that never receive
+        # a gradient (e.g. the unused context up-sampling layers of levels 0 and 1) are discovered on the
+        # first step, which reduces everything after backward instead.
         self._buckets = []
         self._comm_stream = None
+        self._on_cuda = dev.type == "cuda"
         if world_size > 1:
-            self._comm_stream = torch.cuda.Stream(device=dev)
+            if self._on_cuda:
+                self._comm_stream = torch.cuda.Stream(device=dev)
             bounds = [int(round(total * k / n_buckets)) for k in range(n_buckets + 1)]
-            # snap bucket bounds to parameter boundaries
             starts = [s0 for (s0, _) in self._spans]
             snapped = [0] + [min(starts, key=lambda s0: abs(s0 - b)) for b in bounds[1:-1]] + [total]
             snapped = sorted(set(snapped))
             self._buckets = [(snapped[i], snapped[i + 1]) for i in range(len(snapped) - 1)]
-            self._pending = [0] * len(self._buckets)
             self._bucket_of = []
             for (s, e) in self._spans:
                 self._bucket_of.append(next(i for i, (bs, be) in enumerate(self._buckets) if bs <= s < be))
-            self._counts = [self._bucket_of.count(i) for i in range(len(self._buckets))]
+            self._counts = None          # per-bucket number of parameters that do get gradients
+            self._seen = set()
+            self._pending = [0] * len(self._buckets)
+            self.reduced_log = []        # bucket ids in the order their all-reduce was issued (last step)
             for idx, p in enumerate(self.params):
-                p.register_post_accumulate_grad_hook(self._make_hook(self._bucket_of[idx]))
+                p.register_post_accumulate_grad_hook(self._make_hook(idx))
         self._graph = None
         self.launches_per_step = None
         self._static_in = None
         self._static_out = None
 
     # ---------------------------------------------------------------- gradient all-reduce
-    def _make_hook(self, b):
+    def _make_hook(self, idx):
+        b = self._bucket_of[idx]
+
         def hook(_param):
+            if self._counts is None:     # discovery step
+                self._seen.add(idx)
+                return
             self._pending[b] -= 1
             if self._pending[b] == 0:
                 self._launch_allreduce(b)
@@ -74,16 +84,35 @@ class UFlowTrainStep:
 
     def _launch_allreduce(self, b):
         s, e = self._buckets[b]
-        cur = torch.cuda.current_stream()
-        self._comm_stream.wait_stream(cur)
-        with torch.cuda.stream(self._comm_stream):
-            dist.all_reduce(self.flat_grad[s:e], op=dist.ReduceOp.AVG)
+        self.reduced_log.append(b)
+        if self._on_cuda:
+            self._comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm_stream):
+                dist.all_reduce(self.flat_grad[s:e], op=dist.ReduceOp.AVG)
+        else:                            # gloo (CPU tests): no AVG op
+            dist.all_reduce(self.flat_grad[s:e])
+            self.flat_grad[s:e] /= self.world_size
+
+    def _finish_allreduce(self):
+        if self._counts is None:
+            # first step: reduce every bucket now and fix the per-bucket counts for the following steps
+            for b in range(len(self._buckets)):
+                self._launch_allreduce(b)
+            self._counts = [sum(1 for i in self._seen if self._bucket_of[i] == b) for b in range(len(self._buckets))]
+        else:
+            for b, c in enumerate(self._counts):
+                if c == 0:               # a bucket made only of gradient-less parameters: nothing to wait for
+                    pass
+        if self._on_cuda:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
 
     # ---------------------------------------------------------------- the step
     def _step_impl(self, img_pair):
         if self.world_size > 1:
             self.flat_grad.zero_()
-            self._pending = list(self._counts)
+            self.reduced_log = []
+            if self._counts is not None:
+                self._pending = list(self._counts)
         else:
             for p in self.params:
                 p.grad = None
@@ -92,7 +121,7 @@ class UFlowTrainStep:
         loss, l_ph, l_sm, flow_mean, _ = self.loss_fn(flows, img_pair)
         loss.backward()
         if self.world_size > 1:
-            torch.cuda.current_stream().wait_stream(self._comm_stream)
+            self._finish_allreduce()
         self.optimizer.step()
         return torch.stack([loss.detach(), l_ph.detach(), l_sm.detach(), flow_mean.detach()])
 
