@@ -125,6 +125,62 @@ def main():
             report("warp_fwd", (B, C, H, W), px * (8 * C + 8), px * C * 8, *time_graph(mk("fwd"), px * (8 * C + 8)))
             report("warp_bwd", (B, C, H, W), px * (12 * C + 16), px * C * 16, *time_graph(mk("bwd"), px * (12 * C + 16)))
             report("warp_bwdF", (B, C, H, W), px * (8 * C + 16), px * C * 16, *time_graph(mk("bwdF"), px * (8 * C + 16)))
+    if args.what in ("census", "all"):
+        cshapes = shapes if args.shapes else [(8, 3, 384, 512), (32, 3, 448, 1024)]
+        for (B, C, H, W) in cshapes:
+            px = B * H * W
+            npart = lib.arf_census_num_partials(B, H, W)
+
+            def mkc(kind):
+                def make():
+                    a = torch.rand(B, 3, H, W, device="cuda")
+                    b = torch.rand(B, 3, H, W, device="cuda")
+                    m = torch.rand(B, 1, H, W, device="cuda")
+                    ham = torch.empty(B, 1, H, W, device="cuda")
+                    part = torch.empty(2 * npart, device="cuda")
+                    sums = torch.ones(3, device="cuda")
+                    gl = torch.ones(1, device="cuda")
+                    gb = torch.empty_like(b)
+                    if kind == "fwd":
+                        return lambda: lib.arf_census_fwd(a.data_ptr(), b.data_ptr(), m.data_ptr(), ham.data_ptr(),
+                                                          part.data_ptr(), sums.data_ptr(), B, H, W, 7, 1.0, 0.01, 0.4, cs())
+                    lib.arf_census_fwd(a.data_ptr(), b.data_ptr(), m.data_ptr(), ham.data_ptr(), part.data_ptr(),
+                                       sums.data_ptr(), B, H, W, 7, 1.0, 0.01, 0.4, cs())
+                    return lambda: lib.arf_census_bwd(a.data_ptr(), b.data_ptr(), None, ham.data_ptr(), m.data_ptr(),
+                                                      sums.data_ptr(), gl.data_ptr(), None, gb.data_ptr(), B, H, W, 7,
+                                                      1.0, 0.01, 0.4, cs())
+                return make
+            report("census_fwd", (B, 3, H, W), px * 32, px * 640, *time_graph(mkc("fwd"), px * 32))
+            report("census_bwd", (B, 3, H, W), px * 44, px * 1280, *time_graph(mkc("bwd"), px * 44))
+    if args.what in ("stencil", "all"):
+        for (N, k, H, W) in [(32, 3, 112, 256), (8, 3, 96, 128)]:
+            px = N * H * W
+            taps = (k + 1) ** 2
+
+            def mks(kind):
+                def make():
+                    A = torch.randn(N, 2 * taps, H, W, device="cuda")
+                    X = torch.randn(N, 2, H, W, device="cuda")
+                    Y = torch.empty_like(X)
+                    dA, dX = torch.empty_like(A), torch.empty_like(X)
+                    if kind == "fwd":
+                        return lambda: lib.arf_stencil_mv_fwd(A.data_ptr(), X.data_ptr(), Y.data_ptr(), N, H, W, k, 0, cs())
+                    return lambda: lib.arf_stencil_mv_bwd(A.data_ptr(), X.data_ptr(), Y.data_ptr(), dA.data_ptr(),
+                                                          dX.data_ptr(), N, H, W, k, 0, cs())
+                return make
+            report("stencil_fwd", (N, 2 * taps, H, W), px * (8 * taps + 16), px * 4 * taps, *time_graph(mks("fwd"), px * (8 * taps + 16)))
+            report("stencil_bwd", (N, 2 * taps, H, W), px * (16 * taps + 24), px * 8 * taps, *time_graph(mks("bwd"), px * (16 * taps + 24)))
+
+            def mkt():
+                A = 1 + torch.rand(N, 2, H, W, device="cuda")
+                Bc = 0.3 * torch.randn(N, 2, H, W - 1, device="cuda")
+                Cc = 0.3 * torch.randn(N, 2, H - 1, W, device="cuda")
+                Dc = 0.2 * torch.randn(N, 2, H - 1, W - 1, device="cuda")
+                X = torch.randn(N, 2, H, W, device="cuda")
+                Y = torch.empty_like(X)
+                return lambda: lib.arf_trisolve(A.data_ptr(), Bc.data_ptr(), Cc.data_ptr(), Dc.data_ptr(), X.data_ptr(),
+                                                Y.data_ptr(), N * 2, H, W, 0, cs())
+            report("trisolve", (N, 2, H, W), N * 2 * H * W * 24, N * 2 * H * W * 8, *time_graph(mkt, N * 2 * H * W * 24))
     if args.csv:
         os.makedirs(os.path.dirname(args.csv), exist_ok=True)
         with open(args.csv, "w") as f:

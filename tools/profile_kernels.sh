@@ -1,0 +1,22 @@
+#!/bin/bash
+# ncu --set full captures of the hot kernels (one launch each, after a plain run of the same command).
+# usage: tools/profile_kernels.sh <tag>      (run under gpurun; reports land in gpurun_out/)
+set -u
+TAG=${1:-r1}
+OUT=gpurun_out
+mkdir -p $OUT
+prof () {  # name kernel-regex microbench-args...
+  local name=$1; local regex=$2; shift 2
+  python tools/microbench.py "$@" > $OUT/plain_${name}.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:$regex -s 3 -c 1 \
+      -o $OUT/${name}_${TAG} -f python tools/microbench.py "$@" > $OUT/ncu_${name}.log 2>&1
+  tail -1 $OUT/plain_${name}.log
+}
+prof corr_fwd corr_fwd_md4 corr_fwd --shapes 64x32x96x128
+prof corr_bwd1 'corr_bwd_md4<\(bool\)0' corr_bwd --shapes 64x32x96x128
+prof corr_bwd2 'corr_bwd_md4<\(bool\)1' corr_bwd --shapes 64x32x96x128
+prof warp_fwd warp_fwd_kernel warp --shapes 64x32x96x128
+prof warp_bwd warp_bwd_kernel warp --shapes 64x32x96x128
+prof census_fwd census_fwd_kernel census --shapes 8x3x384x512
+prof census_bwd census_bwd_kernel census --shapes 8x3x384x512
+ls -la $OUT/*.ncu-rep
