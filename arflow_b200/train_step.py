@@ -1,5 +1,15 @@
 """One UFlow training step (model forward, UFlowLoss, backward, Adam) as a replayable unit.
 
+Data-parallel modes (world_size > 1):
+  * eager ("overlap"): a bucket of the flat gradient buffer is all-reduced on a side stream from a
+    post-accumulate hook as soon as its last gradient is written, overlapping the rest of backward;
+  * CUDA graph ("graph_split", the default with use_graph): forward+backward are one captured graph, the
+    all-reduce of the whole flat buffer is ONE eager NCCL call between two graphs, Adam is the second graph.
+    (Capturing the NCCL calls themselves inside the step graph hung on this pool's B200 boxes — torch 2.11 /
+    NCCL 2.28.9, with and without the watchdog's async error handling — so the collective stays outside;
+    22.9 MB over NVLink is ~0.1 ms against a ~29 ms step.)
+
+
 Replaces, for the benchmark driver only, the per-step body of trainer/uflow_trainer.py:30-73 of the
 reference: same maths (PWCFlow -> flows_fw/flows_bw -> cat -> UFlowLoss -> backward -> Adam with the
 config's lr/betas/eps), restructured for the B200:
@@ -62,8 +72,10 @@ class UFlowTrainStep:
             self._seen = set()
             self._pending = [0] * len(self._buckets)
             self.reduced_log = []        # bucket ids in the order their all-reduce was issued (last step)
+            self._hooks_on = not use_graph   # graph_split mode reduces the flat buffer in one call instead
             for idx, p in enumerate(self.params):
                 p.register_post_accumulate_grad_hook(self._make_hook(idx))
+        self._graph_opt = None
         self._graph = None
         self.launches_per_step = None
         self._static_in = None
@@ -74,6 +86,8 @@ class UFlowTrainStep:
         b = self._bucket_of[idx]
 
         def hook(_param):
+            if not self._hooks_on:
+                return
             if self._counts is None:     # discovery step
                 self._seen.add(idx)
                 return
@@ -107,7 +121,7 @@ class UFlowTrainStep:
             torch.cuda.current_stream().wait_stream(self._comm_stream)
 
     # ---------------------------------------------------------------- the step
-    def _step_impl(self, img_pair):
+    def _fwd_bwd(self, img_pair):
         if self.world_size > 1:
             self.flat_grad.zero_()
             self.reduced_log = []
@@ -120,13 +134,21 @@ class UFlowTrainStep:
         flows = [torch.cat([a, b], 1) for a, b in zip(res['flows_fw'], res['flows_bw'])]
         loss, l_ph, l_sm, flow_mean, _ = self.loss_fn(flows, img_pair)
         loss.backward()
-        if self.world_size > 1:
-            self._finish_allreduce()
-        self.optimizer.step()
         return torch.stack([loss.detach(), l_ph.detach(), l_sm.detach(), flow_mean.detach()])
+
+    def _step_impl(self, img_pair):
+        out = self._fwd_bwd(img_pair)
+        if self.world_size > 1:
+            if self._hooks_on:
+                self._finish_allreduce()
+            else:
+                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
+        self.optimizer.step()
+        return out
 
     def capture(self, example, warmup=3):
         """Warm up on a side stream (cuDNN autotune, Adam state, NCCL) and capture the step."""
+        from . import _lib
         self._static_in = example.clone()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -135,11 +157,17 @@ class UFlowTrainStep:
                 self._step_impl(self._static_in)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        from . import _lib
         self._graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self._graph):
-            self._static_out = self._step_impl(self._static_in)
+        if self.world_size > 1:
+            with torch.cuda.graph(self._graph):
+                self._static_out = self._fwd_bwd(self._static_in)
+            self._graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_opt):
+                self.optimizer.step()
+        else:
+            with torch.cuda.graph(self._graph):
+                self._static_out = self._step_impl(self._static_in)
         self.launches_per_step = _lib.launch_count() - n0   # arflow_b200 kernels inside one replay
         torch.cuda.synchronize()
 
@@ -151,4 +179,7 @@ class UFlowTrainStep:
             self.capture(img_pair)
         self._static_in.copy_(img_pair, non_blocking=True)
         self._graph.replay()
+        if self.world_size > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
+            self._graph_opt.replay()
         return self._static_out
