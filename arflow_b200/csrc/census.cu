@@ -42,8 +42,22 @@ __device__ __forceinline__ void load_gray_tile(float (*tile)[kCTW + 2 * R], cons
     }
 }
 
+// Raw MUFU.RSQ / MUFU.RCP: every argument here is >= 0.1, so the denormal/zero fix-up code rsqrtf() and
+// __fdividef() carry (FSETP/FMUL/FSEL per call, ~40% of the instruction stream in the first ncu capture)
+// is dead weight.  Relative error <= 2^-22.
+__device__ __forceinline__ float mufu_rsq(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mufu_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ float ctransform(float d, float& r) {
-    r = rsqrtf(fmaf(d, d, 0.81f));
+    r = mufu_rsq(fmaf(d, d, 0.81f));
     return d * r;
 }
 
@@ -85,7 +99,7 @@ census_fwd_kernel(const float* __restrict__ im_a, const float* __restrict__ im_b
                 float tb = ctransform(gb[ly + dy][lx + dx] - cb, rb);
                 float df = ta - tb;
                 float sq = df * df;
-                h += __fdividef(sq, 0.1f + sq);
+                h = fmaf(sq, mufu_rcp(0.1f + sq), h);
             }
         h *= scale;
         if (x < W && y < H) {
@@ -134,19 +148,21 @@ __global__ void census_finalize_kernel(const float* __restrict__ partials, int n
 }
 
 // d(term)/d(diff_a), d(term)/d(diff_b) of one census offset, times the upstream gradient gh of its pixel
-__device__ __forceinline__ void term_grads(float da, float db, float gh, float& gda, float& gdb) {
+// gh must already carry the constant factor 0.2 * 0.81 (applied once per pixel when the tile is staged).
+template <bool kA, bool kB>
+__device__ __forceinline__ void term_grads(float da, float db, float gh, float& acc_a, float& acc_b, float sign) {
     float ra, rb;
     float ta = ctransform(da, ra);
     float tb = ctransform(db, rb);
     float df = ta - tb;
-    float inv = __fdividef(1.f, fmaf(df, df, 0.1f));
-    float common = gh * 0.2f * df * inv * inv;          // gh * d/d(ta) [sq/(0.1+sq)] = gh * 2*df*0.1/(0.1+sq)^2
-    gda = common * 0.81f * ra * ra * ra;                 // d(ta)/d(da) = 0.81/(0.81+da^2)^1.5
-    gdb = -common * 0.81f * rb * rb * rb;
+    float inv = mufu_rcp(fmaf(df, df, 0.1f));
+    float common = sign * gh * df * inv * inv;          // d/d(ta) [sq/(0.1+sq)] = 2*df*0.1/(0.1+sq)^2
+    if (kA) acc_a = fmaf(common, ra * ra * ra, acc_a);   // d(ta)/d(da) = 0.81/(0.81+da^2)^1.5
+    if (kB) acc_b = fmaf(-common, rb * rb * rb, acc_b);
 }
 
-template <int R>
-__global__ void __launch_bounds__(kCThreads)
+template <int R, bool kA, bool kB>
+__global__ void __launch_bounds__(kCThreads, 3)
 census_bwd_kernel(const float* __restrict__ im_a, const float* __restrict__ im_b, const float* __restrict__ ghamming,
                   const float* __restrict__ hamming, const float* __restrict__ mask, const float* __restrict__ sums,
                   const float* __restrict__ gloss, float* __restrict__ g_a, float* __restrict__ g_b, int B, int H,
@@ -181,7 +197,7 @@ census_bwd_kernel(const float* __restrict__ im_a, const float* __restrict__ im_b
                     float s = h > 0.f ? 1.f : (h < 0.f ? -1.f : 0.f);
                     v = gl * pm * idn * q * __powf(fabsf(h) + eps, q - 1.f) * s;
                 }
-                v *= scale;
+                v *= scale * (0.2f * 0.81f);
             }
             gh[yy][xx] = v;
         }
@@ -197,20 +213,16 @@ census_bwd_kernel(const float* __restrict__ im_a, const float* __restrict__ im_b
         const int cy = ly + R, cx = lx + R;
         const float ca = ga[cy][cx], cb = gb[cy][cx], ghc = gh[cy][cx];
         float acc_a = 0.f, acc_b = 0.f;
-#pragma unroll
+#pragma unroll 1
         for (int dy = -R; dy <= R; ++dy)
 #pragma unroll
             for (int dx = -R; dx <= R; ++dx) {
                 if (dy == 0 && dx == 0) continue;
-                float gda, gdb;
                 // this pixel is the centre, neighbour at +k: diff = I[q+k] - I[q]  -> d/dI[q] = -g
-                term_grads(ga[cy + dy][cx + dx] - ca, gb[cy + dy][cx + dx] - cb, ghc, gda, gdb);
-                acc_a -= gda;
-                acc_b -= gdb;
+                term_grads<kA, kB>(ga[cy + dy][cx + dx] - ca, gb[cy + dy][cx + dx] - cb, ghc, acc_a, acc_b, -1.f);
                 // this pixel is the neighbour of p = q-k: diff = I[q] - I[p]       -> d/dI[q] = +g  (gh[p] = 0 off-image)
-                term_grads(ca - ga[cy - dy][cx - dx], cb - gb[cy - dy][cx - dx], gh[cy - dy][cx - dx], gda, gdb);
-                acc_a += gda;
-                acc_b += gdb;
+                term_grads<kA, kB>(ca - ga[cy - dy][cx - dx], cb - gb[cy - dy][cx - dx], gh[cy - dy][cx - dx], acc_a,
+                                   acc_b, 1.f);
             }
         if (x < W && y < H) {
             size_t o = (size_t)b * 3 * plane + (size_t)y * W + x;
@@ -271,9 +283,21 @@ extern "C" int arf_census_bwd(const float* im_a, const float* im_b, const float*
     if (n < 0) return n;
     cudaStream_t st = (cudaStream_t)stream;
     switch (patch / 2) {
-        case 1: census_bwd_kernel<1><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q); break;
-        case 2: census_bwd_kernel<2><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q); break;
-        case 3: census_bwd_kernel<3><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q); break;
+        case 1:
+            if (g_a && g_b) census_bwd_kernel<1, true, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
+            else if (g_b) census_bwd_kernel<1, false, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
+            else census_bwd_kernel<1, true, false><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
+            break;
+        case 2:
+            if (g_a && g_b) census_bwd_kernel<2, true, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
+            else if (g_b) census_bwd_kernel<2, false, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
+            else census_bwd_kernel<2, true, false><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
+            break;
+        case 3:
+            if (g_a && g_b) census_bwd_kernel<3, true, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
+            else if (g_b) census_bwd_kernel<3, false, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
+            else census_bwd_kernel<3, true, false><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
+            break;
         default: return ARF_EUNSUPPORTED;
     }
     ARF_CHECK_LAUNCH();

@@ -83,74 +83,80 @@ __device__ __forceinline__ void pixel_coords(const float* __restrict__ field, co
     Y = source_index(py, g.nH1, g.Hs, g.pad_mode, g.align, dY);
 }
 
-constexpr int kFwdCG = 4;  // channels per thread in the forward
+// Bilinear tap geometry of one output pixel (ATen grid_sampler_2d): weights already zeroed for taps
+// outside the source, offsets clamped so every load is legal.
+struct Taps {
+    size_t o[4];       // nw, ne, sw, se element offsets inside one source plane
+    float w[4];        // matching weights (0 for out-of-range taps)
+    float fxe, fxw, fys, fyn;
+    bool in[4];
+};
 
+__device__ __forceinline__ void make_taps(float X, float Y, const WarpGeom& g, Taps& t) {
+    float xf = floorf(X), yf = floorf(Y);
+    int xw = (int)xf, yn = (int)yf, xe = xw + 1, ys = yn + 1;
+    t.fxe = (float)xe - X; t.fxw = X - (float)xw; t.fys = (float)ys - Y; t.fyn = Y - (float)yn;
+    bool inw = xw >= 0 && xw < g.Ws, ine = xe >= 0 && xe < g.Ws;
+    bool inn = yn >= 0 && yn < g.Hs, ins = ys >= 0 && ys < g.Hs;
+    t.in[0] = inn && inw; t.in[1] = inn && ine; t.in[2] = ins && inw; t.in[3] = ins && ine;
+    int xwc = min(max(xw, 0), g.Ws - 1), xec = min(max(xe, 0), g.Ws - 1);
+    int ync = min(max(yn, 0), g.Hs - 1), ysc = min(max(ys, 0), g.Hs - 1);
+    t.o[0] = (size_t)ync * g.Ws + xwc; t.o[1] = (size_t)ync * g.Ws + xec;
+    t.o[2] = (size_t)ysc * g.Ws + xwc; t.o[3] = (size_t)ysc * g.Ws + xec;
+    t.w[0] = t.in[0] ? t.fxe * t.fys : 0.f;
+    t.w[1] = t.in[1] ? t.fxw * t.fys : 0.f;
+    t.w[2] = t.in[2] ? t.fxe * t.fyn : 0.f;
+    t.w[3] = t.in[3] ? t.fxw * t.fyn : 0.f;
+}
+
+constexpr int kCU = 4;   // channels whose loads are issued together
+
+// grid = (pixel blocks, channel splits, batch); a thread computes its pixel's coordinates once and walks
+// its channel range four channels (16 independent tap loads) at a time.
 __global__ void __launch_bounds__(256)
 warp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ field, float* __restrict__ y,
-                WarpGeom g) {
+                WarpGeom g, int ch_per_split) {
     const size_t hwo = (size_t)g.Ho * g.Wo, hws = (size_t)g.Hs * g.Ws;
-    const int ngroups = (g.C + kFwdCG - 1) / kFwdCG;
-    const long long total = (long long)g.B * ngroups * hwo;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        int pix = idx % hwo;
-        long long t = idx / hwo;
-        int cg = t % ngroups;
-        int b = t / ngroups;
-        int i = pix / g.Wo, j = pix - i * g.Wo;
-        float X, Y, dX, dY;
-        pixel_coords(field, g, b, i, j, X, Y, dX, dY);
-        const int c0 = cg * kFwdCG;
-        const float* xb = x + ((size_t)b * g.C + c0) * hws;
-        float* yb = y + ((size_t)b * g.C + c0) * hwo + pix;
-        const int nc = min(kFwdCG, g.C - c0);
-        if (g.interp == ARF_INTERP_NEAREST) {
-            int xn = (int)nearbyintf(X), yn = (int)nearbyintf(Y);
-            bool in = xn >= 0 && xn < g.Ws && yn >= 0 && yn < g.Hs;
-            for (int c = 0; c < nc; ++c)
-                yb[c * hwo] = in ? __ldg(xb + c * hws + (size_t)yn * g.Ws + xn) : 0.f;
-            continue;
-        }
-        float xf = floorf(X), yf = floorf(Y);
-        int xw = (int)xf, yn = (int)yf, xe = xw + 1, ys = yn + 1;
-        float wnw = ((float)xe - X) * ((float)ys - Y);
-        float wne = (X - (float)xw) * ((float)ys - Y);
-        float wsw = ((float)xe - X) * (Y - (float)yn);
-        float wse = (X - (float)xw) * (Y - (float)yn);
-        bool inw = xw >= 0 && xw < g.Ws, ine = xe >= 0 && xe < g.Ws;
-        bool inn = yn >= 0 && yn < g.Hs, ins = ys >= 0 && ys < g.Hs;
-        // clamp addresses so all loads are legal, mask through the weights
-        int xwc = min(max(xw, 0), g.Ws - 1), xec = min(max(xe, 0), g.Ws - 1);
-        int ync = min(max(yn, 0), g.Hs - 1), ysc = min(max(ys, 0), g.Hs - 1);
-        if (!(inn && inw)) wnw = 0.f;
-        if (!(inn && ine)) wne = 0.f;
-        if (!(ins && inw)) wsw = 0.f;
-        if (!(ins && ine)) wse = 0.f;
-        size_t onw = (size_t)ync * g.Ws + xwc, one = (size_t)ync * g.Ws + xec;
-        size_t osw = (size_t)ysc * g.Ws + xwc, ose = (size_t)ysc * g.Ws + xec;
-        float v[kFwdCG][4];
+    const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= hwo) return;
+    const int b = blockIdx.z;
+    const int c_lo = blockIdx.y * ch_per_split, c_hi = min(g.C, c_lo + ch_per_split);
+    const int i = (int)(pix / g.Wo), j = (int)(pix - (size_t)i * g.Wo);
+    float X, Y, dX, dY;
+    pixel_coords(field, g, b, i, j, X, Y, dX, dY);
+    const float* xb = x + (size_t)b * g.C * hws;
+    float* yb = y + (size_t)b * g.C * hwo + pix;
+    if (g.interp == ARF_INTERP_NEAREST) {
+        int xn = (int)nearbyintf(X), yn = (int)nearbyintf(Y);
+        bool in = xn >= 0 && xn < g.Ws && yn >= 0 && yn < g.Hs;
+        for (int c = c_lo; c < c_hi; ++c)
+            yb[(size_t)c * hwo] = in ? __ldg(xb + (size_t)c * hws + (size_t)yn * g.Ws + xn) : 0.f;
+        return;
+    }
+    Taps t;
+    make_taps(X, Y, g, t);
+    for (int c0 = c_lo; c0 < c_hi; c0 += kCU) {
+        float v[kCU][4];
 #pragma unroll
-        for (int c = 0; c < kFwdCG; ++c) {
-            if (c < nc) {
-                const float* p = xb + c * hws;
-                v[c][0] = __ldg(p + onw); v[c][1] = __ldg(p + one);
-                v[c][2] = __ldg(p + osw); v[c][3] = __ldg(p + ose);
-            }
-        }
+        for (int u = 0; u < kCU; ++u)
+            if (c0 + u < c_hi) {
+                const float* p = xb + (size_t)(c0 + u) * hws;
 #pragma unroll
-        for (int c = 0; c < kFwdCG; ++c) {
-            if (c < nc) {
-                float o = v[c][0] * wnw;
-                o = fmaf(v[c][1], wne, o);
-                o = fmaf(v[c][2], wsw, o);
-                o = fmaf(v[c][3], wse, o);
-                yb[c * hwo] = o;
+                for (int k = 0; k < 4; ++k) v[u][k] = __ldg(p + t.o[k]);
             }
-        }
+#pragma unroll
+        for (int u = 0; u < kCU; ++u)
+            if (c0 + u < c_hi) {
+                float o = v[u][0] * t.w[0];
+                o = fmaf(v[u][1], t.w[1], o);
+                o = fmaf(v[u][2], t.w[2], o);
+                o = fmaf(v[u][3], t.w[3], o);
+                __stcs(yb + (size_t)(c0 + u) * hwo, o);
+            }
     }
 }
 
-// block = (32 pixels, G channel groups); thread (px, gy) handles channels gy, gy+G, ...
+// block = (32 pixels, G channel groups); thread (px, grp) handles channels grp, grp+G, ... four at a time.
 template <int G>
 __global__ void __launch_bounds__(32 * G)
 warp_bwd_kernel(const float* __restrict__ x, const float* __restrict__ field,
@@ -159,49 +165,53 @@ warp_bwd_kernel(const float* __restrict__ x, const float* __restrict__ field,
     __shared__ float red[2][G][32];
     const size_t hwo = (size_t)g.Ho * g.Wo, hws = (size_t)g.Hs * g.Ws;
     const int lane = threadIdx.x, grp = threadIdx.y;
+    const int b = blockIdx.y;
     const long long nrun = ((long long)hwo + 31) / 32;  // 32-pixel runs per image
-    const long long total = (long long)g.B * nrun;
-    for (long long run = blockIdx.x; run < total; run += gridDim.x) {
-        int b = run / nrun;
-        long long pix = (run - (long long)b * nrun) * 32 + lane;
-        bool live = pix < (long long)hwo;
+    for (long long run = blockIdx.x; run < nrun; run += gridDim.x) {
+        const long long pix = run * 32 + lane;
+        const bool live = pix < (long long)hwo;
         float ax = 0.f, ay = 0.f, dX = 0.f, dY = 0.f;
         if (live) {
-            int i = pix / g.Wo, j = pix - (long long)i * g.Wo;
+            int i = (int)(pix / g.Wo), j = (int)(pix - (long long)i * g.Wo);
             float X, Y;
             pixel_coords(field, g, b, i, j, X, Y, dX, dY);
+            const float* xb = x + (size_t)b * g.C * hws;
+            const float* gb = gy + (size_t)b * g.C * hwo + pix;
             if (g.interp == ARF_INTERP_BILINEAR) {
-                float xf = floorf(X), yf = floorf(Y);
-                int xw = (int)xf, yn = (int)yf, xe = xw + 1, ys = yn + 1;
-                float fxe = (float)xe - X, fxw = X - (float)xw, fys = (float)ys - Y, fyn = Y - (float)yn;
-                bool inw = xw >= 0 && xw < g.Ws, ine = xe >= 0 && xe < g.Ws;
-                bool inn = yn >= 0 && yn < g.Hs, ins = ys >= 0 && ys < g.Hs;
-                bool bnw = inn && inw, bne = inn && ine, bsw = ins && inw, bse = ins && ine;
-                int xwc = min(max(xw, 0), g.Ws - 1), xec = min(max(xe, 0), g.Ws - 1);
-                int ync = min(max(yn, 0), g.Hs - 1), ysc = min(max(ys, 0), g.Hs - 1);
-                size_t onw = (size_t)ync * g.Ws + xwc, one = (size_t)ync * g.Ws + xec;
-                size_t osw = (size_t)ysc * g.Ws + xwc, ose = (size_t)ysc * g.Ws + xec;
-                for (int c = grp; c < g.C; c += G) {
-                    float go = __ldg(gy + ((size_t)b * g.C + c) * hwo + pix);
-                    const float* p = x + ((size_t)b * g.C + c) * hws;
-                    float vnw = bnw ? __ldg(p + onw) : 0.f, vne = bne ? __ldg(p + one) : 0.f;
-                    float vsw = bsw ? __ldg(p + osw) : 0.f, vse = bse ? __ldg(p + ose) : 0.f;
-                    ax += go * ((vne - vnw) * fys + (vse - vsw) * fyn);
-                    ay += go * ((vsw - vnw) * fxe + (vse - vne) * fxw);
-                    if (gx) {
-                        float* q = gx + ((size_t)b * g.C + c) * hws;
-                        if (bnw) atomicAdd(q + onw, go * fxe * fys);
-                        if (bne) atomicAdd(q + one, go * fxw * fys);
-                        if (bsw) atomicAdd(q + osw, go * fxe * fyn);
-                        if (bse) atomicAdd(q + ose, go * fxw * fyn);
+                Taps t;
+                make_taps(X, Y, g, t);
+                for (int c0 = grp; c0 < g.C; c0 += kCU * G) {
+                    float go[kCU], v[kCU][4];
+#pragma unroll
+                    for (int u = 0; u < kCU; ++u) {
+                        const int c = c0 + u * G;
+                        if (c < g.C) {
+                            go[u] = __ldg(gb + (size_t)c * hwo);
+                            const float* p = xb + (size_t)c * hws;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) v[u][k] = t.in[k] ? __ldg(p + t.o[k]) : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kCU; ++u) {
+                        const int c = c0 + u * G;
+                        if (c < g.C) {
+                            ax = fmaf(go[u], (v[u][1] - v[u][0]) * t.fys + (v[u][3] - v[u][2]) * t.fyn, ax);
+                            ay = fmaf(go[u], (v[u][2] - v[u][0]) * t.fxe + (v[u][3] - v[u][1]) * t.fxw, ay);
+                            if (gx) {
+                                float* q = gx + ((size_t)b * g.C + c) * hws;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (t.in[k]) atomicAdd(q + t.o[k], go[u] * t.w[k]);
+                            }
+                        }
                     }
                 }
             } else if (gx) {  // nearest: no field gradient, source gradient is a plain scatter
                 int xn = (int)nearbyintf(X), yn = (int)nearbyintf(Y);
                 if (xn >= 0 && xn < g.Ws && yn >= 0 && yn < g.Hs)
                     for (int c = grp; c < g.C; c += G)
-                        atomicAdd(gx + ((size_t)b * g.C + c) * hws + (size_t)yn * g.Ws + xn,
-                                  __ldg(gy + ((size_t)b * g.C + c) * hwo + pix));
+                        atomicAdd(gx + ((size_t)b * g.C + c) * hws + (size_t)yn * g.Ws + xn, __ldg(gb + (size_t)c * hwo));
             }
         }
         if (gfield) {
@@ -246,8 +256,16 @@ extern "C" int arf_warp_fwd(const float* x, const float* field, float* y, int B,
     WarpGeom g;
     int rc = make_geom(g, B, C, Hs, Ws, Ho, Wo, nW1, nH1, field_kind, interp, pad_mode, align_corners);
     if (rc) return rc;
-    long long total = (long long)B * ((C + kFwdCG - 1) / kFwdCG) * Ho * Wo;
-    warp_fwd_kernel<<<arf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x, field, y, g);
+    if (B > 65535) return ARF_EINVAL;
+    // enough threads to fill the machine (~2 waves of 2048 threads/SM) before splitting channels further
+    const long long px = (long long)B * Ho * Wo;
+    long long want = (2LL * ARF_NUM_SMS * 2048 + px - 1) / px;
+    int groups = (C + kCU - 1) / kCU;
+    int nsplit = (int)(want < 1 ? 1 : (want > groups ? groups : want));
+    int ch_per_split = ((groups + nsplit - 1) / nsplit) * kCU;
+    nsplit = (C + ch_per_split - 1) / ch_per_split;
+    dim3 grid(arf_cdiv((long long)Ho * Wo, 256), nsplit, B);
+    warp_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, field, y, g, ch_per_split);
     ARF_CHECK_LAUNCH();
     return ARF_OK;
 }
@@ -265,10 +283,14 @@ extern "C" int arf_warp_bwd(const float* x, const float* field, const float* gy,
         if (e != cudaSuccess) return (int)e;
     }
     if (!gx && !gfield) return ARF_OK;
-    long long runs = (long long)B * (((long long)Ho * Wo + 31) / 32);
-    int grid = (int)(runs < (long long)ARF_NUM_SMS * 16 ? runs : (long long)ARF_NUM_SMS * 16);
+    if (B > 65535) return ARF_EINVAL;
+    const long long runs = ((long long)Ho * Wo + 31) / 32;
+    const long long cap = ((long long)ARF_NUM_SMS * 32 + B - 1) / B;
+    dim3 grid((unsigned)(runs < cap ? runs : cap), B);
     if (C <= 4) {
         warp_bwd_kernel<1><<<grid, dim3(32, 1), 0, st>>>(x, field, gy, gx, gfield, g);
+    } else if (C <= 16) {
+        warp_bwd_kernel<4><<<grid, dim3(32, 4), 0, st>>>(x, field, gy, gx, gfield, g);
     } else {
         warp_bwd_kernel<8><<<grid, dim3(32, 8), 0, st>>>(x, field, gy, gx, gfield, g);
     }

@@ -61,5 +61,12 @@ def test_against_reference_cuda_kernels(ref_cuda, shape, geom):
     # the reference's own self-check bar is atol 1e-7 on N(0,1) inputs (correlation_native.py:64); both sides are
     # fp32 sums in different orders, so the bar here is the north_star's 1e-5 / 1e-4 relative
     assert_close(out, r_out, 1e-5, "cost volume vs reference CUDA")
+    if s1 != 1:
+        # The reference's backward kernels index their output pixel as blockIdx * stride1 over a grid of
+        # (H, W, C) blocks (correlation_cuda_kernel.cu:129-130, 224-225, 485-486): for stride1 > 1 they write
+        # out of bounds into neighbouring planes and leave odd pixels untouched — undefined behaviour, nothing
+        # to be bit-compatible with.  arflow_b200 evaluates the same window formulas at every pixel instead
+        # (pinned by the C oracle); only the forward is compared here.
+        return
     assert_close(g1, r_g1, 1e-4, "grad input1 vs reference CUDA")
     assert_close(g2, r_g2, 1e-4, "grad input2 vs reference CUDA")
