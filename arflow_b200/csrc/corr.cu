@@ -97,26 +97,30 @@ constexpr int kD = 2 * kMD + 1;    // 9
 constexpr int kHW = kTW + 2 * kMD; // 40 halo width
 constexpr int kHH = kTH + 2 * kMD; // 16 halo height
 constexpr int kCc = 8;             // channels per pipeline stage
-constexpr int kConsumerWarps = kD;                    // warp w <-> dx = w-4
-constexpr int kFwdThreads = 32 * (kConsumerWarps + 1);  // + 1 producer warp
-
-struct __align__(128) FwdStage {
-    float s1[kCc][kTH][kTW];   // f1 tile                    8 KB
-    float s2[kCc][kHH][kHW];   // f2 tile with 4-px halo    20 KB
+// kRG row groups of 8 rows share one CTA tile (and its f2 halo): consumer warp w <-> (row group w/9, dx = w%9 - 4)
+template <int kRG>
+struct __align__(128) FwdStageT {
+    float s1[kCc][kTH * kRG][kTW];             // f1 tile                    8 KB per row group
+    float s2[kCc][kTH * kRG + 2 * kMD][kHW];   // f2 tile with 4-px halo    20 KB (RG=1) / 30 KB (RG=2)
 };
-constexpr uint32_t kFwdStageBytes = sizeof(FwdStage);
-constexpr size_t fwd_smem(int stages) { return stages * sizeof(FwdStage) + 2 * stages * sizeof(uint64_t); }
+template <int kRG>
+constexpr size_t fwd_smem(int stages) { return stages * sizeof(FwdStageT<kRG>) + 2 * stages * sizeof(uint64_t); }
 
 // Persistent, warp-specialised: warp 9 streams (f1 tile, f2 halo tile) channel chunks through a
 // kStages-deep shared-memory ring (TMA with hardware zero fill when kTma, else zero-filling
 // cp.async), warps 0..8 consume.  The ring keeps running across tile boundaries, so the loads of
 // the next tile overlap the 72 output stores per thread of the current one.
-template <bool kTma, int kStg, int kMinBlocks, int kUnroll>
-__global__ void __launch_bounds__(kFwdThreads, kMinBlocks)
+template <bool kTma, int kRG, int kStg, int kMinBlocks, int kUnroll>
+__global__ void __launch_bounds__(32 * (kD * kRG + 1), kMinBlocks)
 corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
              const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ out,
              int B, int C, int H, int W, int tiles_x, int tiles_y, float inv_c) {
     constexpr int kStages = kStg;
+    constexpr int kConsumerWarps = kD * kRG;
+    constexpr int kTileH = kTH * kRG;            // CTA tile height
+    constexpr int kHaloH = kTileH + 2 * kMD;
+    using FwdStage = FwdStageT<kRG>;
+    constexpr uint32_t kFwdStageBytes = sizeof(FwdStage);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FwdStage* stg = reinterpret_cast<FwdStage*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(FwdStage));
@@ -146,7 +150,7 @@ corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ C
         uint32_t it = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
-            const int x0 = tx * kTW, y0 = ty * kTH;
+            const int x0 = tx * kTW, y0 = ty * kTileH;
             for (int ch = 0; ch < nchunks; ++ch, ++it) {
                 const int s = it % kStages;
                 const uint32_t ph = (it / kStages) & 1;
@@ -161,15 +165,15 @@ corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ C
                 } else {
                     const float* f1b = f1 + (size_t)b * C * plane;
                     const float* f2b = f2 + (size_t)b * C * plane;
-                    for (int e = lane; e < kCc * kTH * kTW; e += 32) {
-                        int rr = (e / kTW) % kTH, cc = e / (kTW * kTH);
+                    for (int e = lane; e < kCc * kTileH * kTW; e += 32) {
+                        int rr = (e / kTW) % kTileH, cc = e / (kTW * kTileH);
                         int gx = x0 + lane, gy = y0 + rr, gc = c0 + cc;
                         bool ok = gc < C && gy < H && gx < W;
                         arf::cp_async_4_zfill(&stg[s].s1[cc][rr][lane],
                                               ok ? f1b + gc * plane + (size_t)gy * W + gx : f1b, ok);
                     }
-                    for (int e = lane; e < kCc * kHH * kHW; e += 32) {
-                        int xx = e % kHW, rr = (e / kHW) % kHH, cc = e / (kHW * kHH);
+                    for (int e = lane; e < kCc * kHaloH * kHW; e += 32) {
+                        int xx = e % kHW, rr = (e / kHW) % kHaloH, cc = e / (kHW * kHaloH);
                         int gx = x0 + xx - kMD, gy = y0 + rr - kMD, gc = c0 + cc;
                         bool ok = gc < C && gy >= 0 && gy < H && gx >= 0 && gx < W;
                         arf::cp_async_4_zfill(&stg[s].s2[cc][rr][xx],
@@ -183,11 +187,12 @@ corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ C
     }
 
     // ---------------------------------------------------------------- consumer warps
-    const int wdx = warp;  // 0..8 -> dx = wdx-4
+    const int wdx = warp % kD;         // 0..8 -> dx = wdx-4
+    const int r0 = (warp / kD) * kTH;  // first row of this warp's row group inside the CTA tile
     uint32_t it = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
-        const int x0 = tx * kTW, y0 = ty * kTH;
+        const int x0 = tx * kTW, y0 = ty * kTileH + r0;
 
         float acc[kTH][kD];
 #pragma unroll
@@ -204,9 +209,9 @@ corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ C
             for (int cc = 0; cc < kCc; ++cc) {
                 float a[kTH], bb[kHH];
 #pragma unroll
-                for (int r = 0; r < kTH; ++r) a[r] = S.s1[cc][r][lane];
+                for (int r = 0; r < kTH; ++r) a[r] = S.s1[cc][r0 + r][lane];
 #pragma unroll
-                for (int k = 0; k < kHH; ++k) bb[k] = S.s2[cc][k][lane + wdx];
+                for (int k = 0; k < kHH; ++k) bb[k] = S.s2[cc][r0 + k][lane + wdx];
 #pragma unroll
                 for (int r = 0; r < kTH; ++r)
 #pragma unroll
@@ -503,34 +508,38 @@ extern "C" int arf_corr_fwd(const float* f1, const float* f2, float* out, int B,
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (is_fast(g)) {
-        const int tiles_x = arf_cdiv(W, kTW), tiles_y = arf_cdiv(H, kTH);
+        const int rg = (g_variant == 3 || g_variant == 4) ? 2 : 1;
+        const int tiles_x = arf_cdiv(W, kTW), tiles_y = arf_cdiv(H, kTH * rg);
         const long long ntiles = (long long)tiles_x * tiles_y * B;
         if (ntiles > 0x7fffffffLL) return ARF_EINVAL;
         CUtensorMap m1, m2;
         bool tma = !g_force_no_tma && arf::tma_ok_nchw(f1, W) && arf::tma_ok_nchw(f2, W) &&
-                   arf::make_map_nchw(&m1, f1, B, C, H, W, kTW, kTH, kCc) &&
-                   arf::make_map_nchw(&m2, f2, B, C, H, W, kHW, kHH, kCc);
+                   arf::make_map_nchw(&m1, f1, B, C, H, W, kTW, kTH * rg, kCc) &&
+                   arf::make_map_nchw(&m2, f2, B, C, H, W, kHW, kTH * rg + 2 * kMD, kCc);
         if (!tma) {
             memset(&m1, 0, sizeof(m1));
             memset(&m2, 0, sizeof(m2));
         }
         const float inv_c = 1.0f / (float)C;
-#define ARF_LAUNCH_FWD(TMA, STG, MINB, UNR)                                                                  \
+#define ARF_LAUNCH_FWD(TMA, RG, STG, MINB, UNR)                                                              \
     do {                                                                                                     \
-        auto kern = corr_fwd_md4<TMA, STG, MINB, UNR>;                                                       \
+        auto kern = corr_fwd_md4<TMA, RG, STG, MINB, UNR>;                                                   \
         static bool attr = false;                                                                            \
         if (!attr) {                                                                                         \
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(STG));     \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<RG>(STG)); \
             attr = true;                                                                                     \
         }                                                                                                    \
         const int grid = (int)(ntiles < (MINB) * ARF_NUM_SMS ? ntiles : (MINB) * ARF_NUM_SMS);               \
-        kern<<<grid, kFwdThreads, fwd_smem(STG), st>>>(m1, m2, f1, f2, out, B, C, H, W, tiles_x, tiles_y, inv_c); \
+        kern<<<grid, 32 * (kD * RG + 1), fwd_smem<RG>(STG), st>>>(m1, m2, f1, f2, out, B, C, H, W, tiles_x,  \
+                                                                  tiles_y, inv_c);                           \
     } while (0)
-        if (!tma) ARF_LAUNCH_FWD(false, 3, 2, 1);
-        else if (g_variant == 1) ARF_LAUNCH_FWD(true, 6, 1, 2);
-        else if (g_variant == 2) ARF_LAUNCH_FWD(true, 6, 1, 1);
-        else ARF_LAUNCH_FWD(true, 3, 2, 1);
+        if (!tma) ARF_LAUNCH_FWD(false, 1, 3, 2, 1);
+        else if (g_variant == 3) ARF_LAUNCH_FWD(true, 2, 4, 1, 1);
+        else if (g_variant == 4) ARF_LAUNCH_FWD(true, 2, 3, 1, 1);
+        else ARF_LAUNCH_FWD(true, 1, 3, 2, 1);
 #undef ARF_LAUNCH_FWD
+        ARF_CHECK_LAUNCH();
+        return ARF_OK;
     } else {
         long long total = (long long)B * g.D * g.D * g.oH * g.oW;
         corr_fwd_literal<<<arf_grid_1d(total, 256), 256, 0, st>>>(f1, f2, out, g);

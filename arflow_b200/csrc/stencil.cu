@@ -17,84 +17,80 @@ namespace {
 // ---------------------------------------------------------------------------- mat-vec -----
 // transposed = 0:  Y[p] = sum_t A[t][p - o_t] * X[p - o_t]        (o_t = (i,j), inside the image)
 // transposed = 1:  Y[p] = sum_t A[t][p]       * X[p + o_t]
-__global__ void __launch_bounds__(256)
-stencil_mv_kernel(const float* __restrict__ A, const float* __restrict__ X, float* __restrict__ Y, int N, int H,
-                  int W, int k, int transposed) {
+// grid = (x blocks, y, n*2 + ch): no integer division; K1 = k+1 is a template parameter for the common
+// supports (k = 1, 3) so the (k+1)^2 coefficient loads of a pixel are all in flight together.
+template <int K1T>
+__global__ void __launch_bounds__(128)
+stencil_mv_kernel(const float* __restrict__ A, const float* __restrict__ X, float* __restrict__ Y, int H, int W,
+                  int k1_rt, int transposed) {
+    const int k1 = K1T > 0 ? K1T : k1_rt;
     const size_t hw = (size_t)H * W;
-    const int k1 = k + 1;
-    const long long total = (long long)N * 2 * hw;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        int x = idx % W;
-        long long t = idx / W;
-        int y = t % H; t /= H;
-        int ch = t & 1;
-        long long n = t >> 1;
-        const float* An = A + n * 2 * k1 * k1 * hw + ch * hw;
-        const float* Xn = X + (n * 2 + ch) * hw;
-        float acc = 0.f;
-        for (int i = 0; i < k1; ++i)
-            for (int j = 0; j < k1; ++j) {
-                int tap = i * k1 + j;
-                if (!transposed) {
-                    int ys = y - i, xs = x - j;
-                    if (ys >= 0 && xs >= 0) {
-                        size_t o = (size_t)ys * W + xs;
-                        acc = fmaf(__ldg(An + (size_t)tap * 2 * hw + o), __ldg(Xn + o), acc);
-                    }
-                } else {
-                    // the reference slices A[..., 0:-i, 0:-j]: the tap exists where p + o stays inside
-                    int ys = y + i, xs = x + j;
-                    if (ys < H && xs < W)
-                        acc = fmaf(__ldg(An + (size_t)tap * 2 * hw + (size_t)y * W + x), __ldg(Xn + (size_t)ys * W + xs), acc);
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const size_t n = blockIdx.z >> 1;
+    const int ch = blockIdx.z & 1;
+    const float* An = A + (n * 2 * k1 * k1 + ch) * hw;
+    const float* Xn = X + (n * 2 + ch) * hw;
+    const size_t p = (size_t)y * W + x;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < k1; ++i)
+#pragma unroll
+        for (int j = 0; j < k1; ++j) {
+            const size_t to = (size_t)(i * k1 + j) * 2 * hw;
+            if (!transposed) {
+                if (y - i >= 0 && x - j >= 0) {
+                    size_t o = p - (size_t)i * W - j;
+                    acc = fmaf(arf_ldg_stream(An + to + o), __ldg(Xn + o), acc);
                 }
+            } else {
+                // the reference slices A[..., 0:-i, 0:-j]: the tap exists where p + o stays inside
+                if (y + i < H && x + j < W)
+                    acc = fmaf(arf_ldg_stream(An + to + p), __ldg(Xn + p + (size_t)i * W + j), acc);
             }
-        Y[idx] = acc;
-    }
+        }
+    Y[(n * 2 + ch) * hw + p] = acc;
 }
 
 // Backward of both products in one sweep over A:
 //   transposed = 0 (y = L x):    dX[p] = sum_t A[t][p] * gY[p + o_t],    dA[t][p] = X[p] * gY[p + o_t]
 //   transposed = 1 (y = L^T x):  dX[p] = sum_t A[t][p - o_t] * gY[p - o_t],  dA[t][p] = gY[p] * X[p + o_t]
-__global__ void __launch_bounds__(256)
+template <int K1T>
+__global__ void __launch_bounds__(128)
 stencil_mv_bwd_kernel(const float* __restrict__ A, const float* __restrict__ X, const float* __restrict__ gY,
-                      float* __restrict__ dA, float* __restrict__ dX, int N, int H, int W, int k, int transposed) {
+                      float* __restrict__ dA, float* __restrict__ dX, int H, int W, int k1_rt, int transposed) {
+    const int k1 = K1T > 0 ? K1T : k1_rt;
     const size_t hw = (size_t)H * W;
-    const int k1 = k + 1;
-    const long long total = (long long)N * 2 * hw;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        int x = idx % W;
-        long long t = idx / W;
-        int y = t % H; t /= H;
-        int ch = t & 1;
-        long long n = t >> 1;
-        const size_t p = (size_t)y * W + x;
-        const float* An = A + n * 2 * k1 * k1 * hw + ch * hw;
-        float* dAn = dA ? dA + n * 2 * k1 * k1 * hw + ch * hw : nullptr;
-        const float* Xn = X + (n * 2 + ch) * hw;
-        const float* Gn = gY + (n * 2 + ch) * hw;
-        const float xp = __ldg(Xn + p), gp = __ldg(Gn + p);
-        float acc = 0.f;
-        for (int i = 0; i < k1; ++i)
-            for (int j = 0; j < k1; ++j) {
-                const size_t to = (size_t)(i * k1 + j) * 2 * hw;
-                if (!transposed) {
-                    bool in = (y + i < H) && (x + j < W);
-                    float g = in ? __ldg(Gn + p + (size_t)i * W + j) : 0.f;
-                    if (dX) acc = fmaf(__ldg(An + to + p), g, acc);
-                    if (dAn) dAn[to + p] = xp * g;
-                } else {
-                    bool in = (y + i < H) && (x + j < W);
-                    if (dAn) dAn[to + p] = in ? gp * __ldg(Xn + p + (size_t)i * W + j) : 0.f;
-                    if (dX && y - i >= 0 && x - j >= 0) {
-                        size_t o = p - (size_t)i * W - j;
-                        acc = fmaf(__ldg(An + to + o), __ldg(Gn + o), acc);
-                    }
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const size_t n = blockIdx.z >> 1;
+    const int ch = blockIdx.z & 1;
+    const size_t p = (size_t)y * W + x;
+    const float* An = A + (n * 2 * k1 * k1 + ch) * hw;
+    float* dAn = dA ? dA + (n * 2 * k1 * k1 + ch) * hw : nullptr;
+    const float* Xn = X + (n * 2 + ch) * hw;
+    const float* Gn = gY + (n * 2 + ch) * hw;
+    const float xp = __ldg(Xn + p), gp = __ldg(Gn + p);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < k1; ++i)
+#pragma unroll
+        for (int j = 0; j < k1; ++j) {
+            const size_t to = (size_t)(i * k1 + j) * 2 * hw;
+            const bool in = (y + i < H) && (x + j < W);
+            if (!transposed) {
+                float g = in ? __ldg(Gn + p + (size_t)i * W + j) : 0.f;
+                if (dX) acc = fmaf(arf_ldg_stream(An + to + p), g, acc);
+                if (dAn) __stcs(dAn + to + p, xp * g);
+            } else {
+                if (dAn) __stcs(dAn + to + p, in ? gp * __ldg(Xn + p + (size_t)i * W + j) : 0.f);
+                if (dX && y - i >= 0 && x - j >= 0) {
+                    size_t o = p - (size_t)i * W - j;
+                    acc = fmaf(arf_ldg_stream(An + to + o), __ldg(Gn + o), acc);
                 }
             }
-        if (dX) dX[idx] = acc;
-    }
+        }
+    if (dX) dX[(n * 2 + ch) * hw + p] = acc;
 }
 
 // ---------------------------------------------------------------------------- wavefront ---
@@ -107,6 +103,10 @@ stencil_mv_bwd_kernel(const float* __restrict__ A, const float* __restrict__ X, 
 // Thread t owns logical row t (rows are processed in logical coordinates li = i - r_lo or reflected).
 // unit_rhs: X = e_(r_lo,c_lo) (inverse-diagonal mode), Y is not stored, the sum of squares is returned.
 // Block size = rows rounded up to a warp; sY holds the last two diagonals: sY[2][blockDim.x + 1].
+// Measured (B200, 64 systems of 112x256): 0.6 us per anti-diagonal.  The limiter is not DRAM latency but L1
+// wavefronts: thread <-> row makes every coefficient load touch 32 different sectors (5 arrays x 4 warps x 32
+// = 640 L1 wavefronts per step); a deeper register prefetch ring was tried and is slower (274 vs 219 us).
+// Next step (round 2): thread <-> column with a per-row affine scan, which makes all loads row-contiguous.
 template <bool kUpper, bool kUnit>
 __device__ float wavefront(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ C,
                            const float* __restrict__ D, const float* __restrict__ X, float* __restrict__ Y, int M,
@@ -200,8 +200,13 @@ __global__ void inv_diag_kernel(const float* __restrict__ A, const float* __rest
 extern "C" int arf_stencil_mv_fwd(const float* A, const float* X, float* Y, int N, int H, int W, int k,
                                   int transposed, void* stream) {
     ARF_REQUIRE(A && X && Y && N > 0 && H > 0 && W > 0 && k >= 0 && k <= 15);
-    long long total = (long long)N * 2 * H * W;
-    stencil_mv_kernel<<<arf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(A, X, Y, N, H, W, k, transposed ? 1 : 0);
+    ARF_REQUIRE(H <= 65535 && 2LL * N <= 65535);
+    dim3 grid(arf_cdiv(W, 128), H, 2 * N);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tr = transposed ? 1 : 0;
+    if (k == 1) stencil_mv_kernel<2><<<grid, 128, 0, st>>>(A, X, Y, H, W, 2, tr);
+    else if (k == 3) stencil_mv_kernel<4><<<grid, 128, 0, st>>>(A, X, Y, H, W, 4, tr);
+    else stencil_mv_kernel<0><<<grid, 128, 0, st>>>(A, X, Y, H, W, k + 1, tr);
     ARF_CHECK_LAUNCH();
     return ARF_OK;
 }
@@ -209,10 +214,14 @@ extern "C" int arf_stencil_mv_fwd(const float* A, const float* X, float* Y, int 
 extern "C" int arf_stencil_mv_bwd(const float* A, const float* X, const float* gY, float* dA, float* dX, int N, int H,
                                   int W, int k, int transposed, void* stream) {
     ARF_REQUIRE(A && X && gY && N > 0 && H > 0 && W > 0 && k >= 0 && k <= 15);
+    ARF_REQUIRE(H <= 65535 && 2LL * N <= 65535);
     if (!dA && !dX) return ARF_OK;
-    long long total = (long long)N * 2 * H * W;
-    stencil_mv_bwd_kernel<<<arf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(A, X, gY, dA, dX, N, H, W, k,
-                                                                                     transposed ? 1 : 0);
+    dim3 grid(arf_cdiv(W, 128), H, 2 * N);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tr = transposed ? 1 : 0;
+    if (k == 1) stencil_mv_bwd_kernel<2><<<grid, 128, 0, st>>>(A, X, gY, dA, dX, H, W, 2, tr);
+    else if (k == 3) stencil_mv_bwd_kernel<4><<<grid, 128, 0, st>>>(A, X, gY, dA, dX, H, W, 4, tr);
+    else stencil_mv_bwd_kernel<0><<<grid, 128, 0, st>>>(A, X, gY, dA, dX, H, W, k + 1, tr);
     ARF_CHECK_LAUNCH();
     return ARF_OK;
 }
