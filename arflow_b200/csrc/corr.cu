@@ -114,7 +114,9 @@ template <bool kTma, int kRG, int kStg, int kMinBlocks, int kUnroll>
 __global__ void __launch_bounds__(32 * (kD * kRG + 1), kMinBlocks)
 corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
              const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ out,
-             int B, int C, int H, int W, int tiles_x, int tiles_y, float inv_c) {
+             int B, int C, int H, int W, int tiles_x, int tiles_y, float inv_c, int probe) {
+    // probe (tuning only): 1 = consumers skip the FFMA loop and the stores (pure TMA streaming rate),
+    //                      2 = skip only the stores, 3 = skip only the FFMA loop
     constexpr int kStages = kStg;
     constexpr int kConsumerWarps = kD * kRG;
     constexpr int kTileH = kTH * kRG;            // CTA tile height
@@ -205,6 +207,9 @@ corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ C
             const uint32_t ph = (it / kStages) & 1;
             arf::mbar_wait(&full[s], ph);
             const FwdStage& S = stg[s];
+            if (probe == 1 || probe == 3) {
+                acc[0][0] += S.s1[0][r0][lane] + S.s2[0][r0][lane + wdx];
+            } else
 #pragma unroll kUnroll
             for (int cc = 0; cc < kCc; ++cc) {
                 float a[kTH], bb[kHH];
@@ -221,6 +226,10 @@ corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ C
             if (lane == 0) arf::mbar_arrive(&empty[s]);
         }
 
+        if (probe == 1 || probe == 2) {
+            if (acc[0][0] == 123.456f) out[0] = acc[1][1];   // keep the work alive
+            continue;
+        }
         // epilogue: 72 coalesced 128-byte row stores per warp; mean over channels = sum * (1/C)
         const int gx = x0 + lane;
         float* op = out + ((size_t)b * (kD * kD) + wdx) * plane + (size_t)y0 * W + gx;
@@ -474,6 +483,7 @@ int make_geom(CorrGeom& g, int B, int C, int H, int W, int pad, int ks, int md, 
     return ARF_OK;
 }
 
+int g_probe = 0;         // test hook: see corr_fwd_md4
 int g_variant = 0;       // test hook: kernel variant selection while tuning
 int g_force_no_tma = 0;  // test hook: exercise the cp.async producer on TMA-capable shapes
 
@@ -486,6 +496,7 @@ inline bool is_fast(const CorrGeom& g) {
 extern "C" int arf_debug_set(int key, int value) {
     if (key == 0) { g_force_no_tma = value; return ARF_OK; }
     if (key == 1) { g_variant = value; return ARF_OK; }
+    if (key == 2) { g_probe = value; return ARF_OK; }
     return ARF_EINVAL;
 }
 
@@ -531,7 +542,7 @@ extern "C" int arf_corr_fwd(const float* f1, const float* f2, float* out, int B,
         }                                                                                                    \
         const int grid = (int)(ntiles < (MINB) * ARF_NUM_SMS ? ntiles : (MINB) * ARF_NUM_SMS);               \
         kern<<<grid, 32 * (kD * RG + 1), fwd_smem<RG>(STG), st>>>(m1, m2, f1, f2, out, B, C, H, W, tiles_x,  \
-                                                                  tiles_y, inv_c);                           \
+                                                                  tiles_y, inv_c, g_probe);                  \
     } while (0)
         if (!tma) ARF_LAUNCH_FWD(false, 1, 3, 2, 1);
         else if (g_variant == 3) ARF_LAUNCH_FWD(true, 2, 4, 1, 1);

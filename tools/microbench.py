@@ -59,11 +59,13 @@ def main():
     ap.add_argument("--csv", default=None)
     ap.add_argument("--shapes", default=None, help="comma list of BxCxHxW")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (debug hook 1)")
+    ap.add_argument("--probe", type=int, default=0, help="corr fwd probe mode (debug hook 2)")
     args = ap.parse_args()
     from arflow_b200 import _lib
     from arflow_b200.correlation import corr_out_dims
     lib = _lib.load()
     lib.arf_debug_set(1, args.variant)
+    lib.arf_debug_set(2, args.probe)
     hbm, src = peaks()
     rows = []
 
