@@ -253,6 +253,14 @@ corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ C
     }
 }
 
+// Tuning record (B=64, C=32, 96x128; probes in corr_fwd_md4): memory side alone (TMA loads + 255 MB of row
+// stores) 82 us, pure TMA streaming 33 us, LDS+FFMA loop alone 131 us, whole kernel 152 us.  The loop is bound by
+// shared-memory bytes per FMA: two alternative register tilings that read operands with LDS.128 along x
+// (12 px x 9 dx per thread, 8-10 shared-memory instructions per 108 FFMA instead of 24 per 72) were built and
+// measured at 118-148 us for the loop — the same 1.7x of their shared-memory-byte bound (~74 B/clk/SM effective)
+// as this kernel — and were dropped.  Getting past it needs fewer shared bytes per FMA (bigger register tiles
+// than the 168-register cap of a 10-warp CTA allows) or the tensor pipe (3xTF32 split), see DESIGN.md.
+
 // ------------------------------------------------------------------ tiled backward, md=4 -
 // g1[c,y,x] = 1/C sum_{dy,dx} gO[(dy,dx),y,x]       * f2[c,y+dy,x+dx]           (kSecond = false, F = f2)
 // g2[c,y,x] = 1/C sum_{dy,dx} gO[(dy,dx),y-dy,x-dx] * f1[c,y-dy,x-dx]           (kSecond = true,  F = f1)

@@ -100,3 +100,4 @@ def test_cp_async_staging_path_matches_tma_path(oracle, shape):
         _lib.call("arf_debug_set", 0, 0)
     assert torch.equal(a, b)
     assert_close(a, oracle.corr_fwd_c(f1.cpu(), f2.cpu()), RTOL_VALUE)
+
