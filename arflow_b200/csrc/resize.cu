@@ -52,10 +52,12 @@ __global__ void resize_bwd_kernel(const float* __restrict__ gout, float* __restr
         long long t = idx / g.Wi;
         int iy = t % g.Hi;
         long long n = t / g.Hi;
-        int oy_lo = max(0, (int)floorf(((float)iy - 1.f + 0.5f) * inv_rh - 0.5f) - 1);
-        int oy_hi = min(g.Ho - 1, (int)ceilf(((float)iy + 1.f + 0.5f) * inv_rh - 0.5f) + 1);
-        int ox_lo = max(0, (int)floorf(((float)ix - 1.f + 0.5f) * inv_rw - 0.5f) - 1);
-        int ox_hi = min(g.Wo - 1, (int)ceilf(((float)ix + 1.f + 0.5f) * inv_rw - 0.5f) + 1);
+        // exact range is [ceil(lo), ceil(hi) - 1]; floor/ceil leave one candidate of slack on each side against
+        // rounding, candidates that do not reference the pixel get weight 0 below
+        int oy_lo = max(0, (int)floorf(((float)iy - 0.5f) * inv_rh - 0.5f));
+        int oy_hi = min(g.Ho - 1, (int)ceilf(((float)iy + 1.5f) * inv_rh - 0.5f));
+        int ox_lo = max(0, (int)floorf(((float)ix - 0.5f) * inv_rw - 0.5f));
+        int ox_hi = min(g.Wo - 1, (int)ceilf(((float)ix + 1.5f) * inv_rw - 0.5f));
         if (iy == 0) oy_lo = 0;            // rows clamped at the top edge all read row 0
         if (ix == 0) ox_lo = 0;
         if (iy == g.Hi - 1) oy_hi = g.Ho - 1;
