@@ -94,6 +94,7 @@ census_fwd_kernel(const float* __restrict__ im_a, const float* __restrict__ im_b
         for (int dy = 0; dy <= 2 * R; ++dy)
 #pragma unroll
             for (int dx = 0; dx <= 2 * R; ++dx) {
+                if (dy == R && dx == R) continue;   // the centre's own term is exactly 0
                 float ra, rb;
                 float ta = ctransform(ga[ly + dy][lx + dx] - ca, ra);
                 float tb = ctransform(gb[ly + dy][lx + dx] - cb, rb);
@@ -147,18 +148,22 @@ __global__ void census_finalize_kernel(const float* __restrict__ partials, int n
     }
 }
 
-// d(term)/d(diff_a), d(term)/d(diff_b) of one census offset, times the upstream gradient gh of its pixel
-// gh must already carry the constant factor 0.2 * 0.81 (applied once per pixel when the tile is staged).
+// Gradient of the two census terms that couple pixel q and its neighbour q+k, in one evaluation.
+// Term "q is the centre, neighbour q+k" has diff d = I[q+k]-I[q]; term "q is the neighbour of centre q+k" has
+// diff -d.  Both share rsqrt(0.81+d^2) and 1/(0.1+df^2) (ta, tb, df only flip sign), so
+//   dL/dI_a[q] += -(gh[q] + gh[q+k]) * df * inv^2 * ra^3          (and the mirror image for I_b)
+// which halves the MUFU and FMA work of evaluating the two terms separately.
+// gsum = gh[q] + gh[q+k]; gh already carries the constant factor 0.2 * 0.81 (applied when the tile is staged).
 template <bool kA, bool kB>
-__device__ __forceinline__ void term_grads(float da, float db, float gh, float& acc_a, float& acc_b, float sign) {
+__device__ __forceinline__ void pair_grads(float da, float db, float gsum, float& acc_a, float& acc_b) {
     float ra, rb;
     float ta = ctransform(da, ra);
     float tb = ctransform(db, rb);
     float df = ta - tb;
     float inv = mufu_rcp(fmaf(df, df, 0.1f));
-    float common = sign * gh * df * inv * inv;          // d/d(ta) [sq/(0.1+sq)] = 2*df*0.1/(0.1+sq)^2
-    if (kA) acc_a = fmaf(common, ra * ra * ra, acc_a);   // d(ta)/d(da) = 0.81/(0.81+da^2)^1.5
-    if (kB) acc_b = fmaf(-common, rb * rb * rb, acc_b);
+    float common = gsum * df * inv * inv;               // d/d(ta) [sq/(0.1+sq)] = 2*df*0.1/(0.1+sq)^2
+    if (kA) acc_a = fmaf(-common, ra * ra * ra, acc_a);  // d(ta)/d(da) = 0.81/(0.81+da^2)^1.5
+    if (kB) acc_b = fmaf(common, rb * rb * rb, acc_b);
 }
 
 template <int R, bool kA, bool kB>
@@ -218,11 +223,9 @@ census_bwd_kernel(const float* __restrict__ im_a, const float* __restrict__ im_b
 #pragma unroll
             for (int dx = -R; dx <= R; ++dx) {
                 if (dy == 0 && dx == 0) continue;
-                // this pixel is the centre, neighbour at +k: diff = I[q+k] - I[q]  -> d/dI[q] = -g
-                term_grads<kA, kB>(ga[cy + dy][cx + dx] - ca, gb[cy + dy][cx + dx] - cb, ghc, acc_a, acc_b, -1.f);
-                // this pixel is the neighbour of p = q-k: diff = I[q] - I[p]       -> d/dI[q] = +g  (gh[p] = 0 off-image)
-                term_grads<kA, kB>(ca - ga[cy - dy][cx - dx], cb - gb[cy - dy][cx - dx], gh[cy - dy][cx - dx], acc_a,
-                                   acc_b, 1.f);
+                // gh is zero off-image, so a neighbour outside the image only contributes this pixel's own term
+                pair_grads<kA, kB>(ga[cy + dy][cx + dx] - ca, gb[cy + dy][cx + dx] - cb, ghc + gh[cy + dy][cx + dx],
+                                   acc_a, acc_b);
             }
         if (x < W && y < H) {
             size_t o = (size_t)b * 3 * plane + (size_t)y * W + x;

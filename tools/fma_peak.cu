@@ -40,6 +40,44 @@ __global__ void fma3_kernel(float* out, const float* in, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// Packed fma.rn.f32x2 (FFMA2, sm_100+): two FMAs per lane per instruction.  Same structure as fma3_kernel:
+// 64 accumulators = 32 register pairs, distinct changing operands.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+template <int PAIRS>
+__global__ void fma2_kernel(float* out, const float* in, int iters) {
+    unsigned long long acc[PAIRS];
+    float x[8], y[8];
+#pragma unroll
+    for (int i = 0; i < PAIRS; ++i) acc[i] = 0ull;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x[i] = in[threadIdx.x + i]; y[i] = in[threadIdx.x + 8 + i]; }
+    for (int it = 0; it < iters; ++it) {
+        unsigned long long xp[4], yp[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { xp[i] = pack2(x[2 * i], x[2 * i + 1]); yp[i] = pack2(y[2 * i], y[2 * i + 1]); }
+#pragma unroll
+        for (int i = 0; i < PAIRS; ++i) ffma2(acc[i], xp[i & 3], yp[(i >> 2) & 3]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] += 1.0f;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PAIRS; ++i) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i]));
+        s += lo + hi;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void mufu_kernel(float* out, float a, int iters) {
     float acc[8];
 #pragma unroll
@@ -84,6 +122,8 @@ int main() {
     printf("{\"kernel\":\"ffma_2reg_ilp16\",\"tflops\":%.2f}\n", n * 32 * 2 / ms / 1e9);
     ms = time_ms([&] { fma3_kernel<64><<<blocks, threads>>>(out, in, iters); });
     printf("{\"kernel\":\"ffma_3reg_ilp64\",\"tflops\":%.2f}\n", n * 64 * 2 / ms / 1e9);
+    ms = time_ms([&] { fma2_kernel<32><<<blocks, threads>>>(out, in, iters); });
+    printf("{\"kernel\":\"ffma2_packed_32pairs\",\"tflops\":%.2f}\n", n * 64 * 2 / ms / 1e9);
     ms = time_ms([&] { mufu_kernel<<<blocks, threads>>>(out, 0.5f, iters); });
     printf("{\"kernel\":\"mufu_rsq\",\"gops\":%.1f}\n", n * 8 / ms / 1e6);
     return 0;
