@@ -85,3 +85,80 @@ def test_identity_and_integer_shift_full_size():
     y = flow_warp(x, f)
     assert_close(y[:, :, 2:, :-3], x[:, :, :-2, 3:], 2e-4)
     assert float(y[:, :, :1].abs().max()) < 1e-3
+
+
+# --------------------------------------------------------------------------- window kernels
+def _variant(v):
+    """arf_debug_set key 3: 0 = automatic choice, 1 = force the direct kernels, 2 = force the window kernels."""
+    from arflow_b200 import _lib
+    _lib.load().arf_debug_set(3, v)
+
+
+@pytest.mark.parametrize("shape,sigma,shift,pad,align", [
+    ((2, 32, 48, 64), 2.0, 0.0, "zeros", True),        # full tiles, vector copies
+    ((1, 3, 96, 128), 2.0, 0.0, "zeros", True),
+    ((1, 7, 33, 50), 2.0, 0.0, "zeros", True),         # ragged tiles, W % 4 != 0 -> 4-byte copies
+    ((1, 20, 40, 72), 30.0, 0.0, "zeros", True),       # wild flow: bounding box over the cap -> per-pixel direct path
+    ((2, 9, 64, 96), 0.7, 37.5, "zeros", True),        # large uniform shift: window far from the tile, partly off-image
+    ((1, 9, 64, 96), 0.7, -200.0, "zeros", True),      # every tap off-image
+    ((1, 12, 48, 64), 6.0, 0.0, "border", True),
+    ((1, 12, 48, 64), 6.0, 0.0, "reflection", False),
+    ((1, 40, 100, 200), 1.0, 3.0, "zeros", False),     # window wider than one 128-byte line, several chunks
+    ((3, 5, 9, 20), 1.0, 0.0, "zeros", True),          # tiny image, one ragged tile
+])
+def test_window_kernels_vs_oracle_and_direct(oracle, shape, sigma, shift, pad, align):
+    """Backward window kernels (staged flow gradient + CSR source gradient), forced on every shape."""
+    B, C, H, W = shape
+    gen = torch.Generator().manual_seed(H * W + C)
+    x = torch.randn(shape, generator=gen)
+    f = torch.randn(B, 2, H, W, generator=gen) * sigma + shift
+    xd, fd = x.clone().requires_grad_(True), f.clone().requires_grad_(True)
+    ref = oracle.warp(xd, fd, kind="flow", pad=pad, align_corners=align)
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1234))
+    rx, rf = torch.autograd.grad((ref * w).sum(), [xd, fd])
+    try:
+        _variant(2)
+        out, gx, gf = _run_flow_warp(x, f, pad=pad, align_corners=align)
+        _variant(1)
+        out_d, gx_d, gf_d = _run_flow_warp(x, f, pad=pad, align_corners=align)
+    finally:
+        _variant(0)
+    assert_close(out, ref, RTOL_VALUE)
+    assert_close(gx, rx, RTOL_GRAD)
+    assert_close(gf, rf, RTOL_GRAD)
+    assert_close(gx, gx_d, 2e-6)
+    assert_close(gf, gf_d, 1e-5)
+
+
+def test_window_kernels_auto_at_benchmark_size():
+    """64x32x96x128 is over the automatic threshold: the window kernels must agree with the direct ones."""
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(64, 32, 96, 128, generator=gen)
+    f = torch.nn.functional.interpolate(torch.randn(64, 2, 12, 16, generator=gen) * 3, scale_factor=8, mode="bilinear")
+    out, gx, gf = _run_flow_warp(x, f)
+    try:
+        _variant(1)
+        out_d, gx_d, gf_d = _run_flow_warp(x, f)
+    finally:
+        _variant(0)
+    assert torch.equal(out, out_d)
+    assert_close(gx, gx_d, 2e-6)
+    assert_close(gf, gf_d, 1e-5)
+
+
+def test_window_flow_grad_only_full_size():
+    """Image warp of the loss (source detached): flow gradient only, 8x3x384x512, smooth flow."""
+    from arflow_b200.warp_utils import flow_warp
+    gen = torch.Generator().manual_seed(11)
+    x = torch.rand(8, 3, 384, 512, generator=gen).cuda()
+    f = torch.nn.functional.interpolate(torch.randn(8, 2, 24, 32, generator=gen) * 6, scale_factor=16,
+                                        mode="bilinear").cuda().requires_grad_(True)
+    w = torch.randn(8, 3, 384, 512, generator=gen).cuda()
+    try:
+        _variant(2)
+        (g_win,) = torch.autograd.grad((flow_warp(x, f) * w).sum(), [f])
+        _variant(1)
+        (g_dir,) = torch.autograd.grad((flow_warp(x, f) * w).sum(), [f])
+    finally:
+        _variant(0)
+    assert_close(g_win, g_dir, 1e-5)

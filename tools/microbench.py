@@ -60,12 +60,17 @@ def main():
     ap.add_argument("--shapes", default=None, help="comma list of BxCxHxW")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (debug hook 1)")
     ap.add_argument("--probe", type=int, default=0, help="corr fwd probe mode (debug hook 2)")
+    ap.add_argument("--flow", default="both", choices=["iid", "smooth", "both"],
+                    help="warp flow field: iid N(0,2^2) px per pixel (config 5, worst case for gathers) or a smooth field "
+                         "(1/8-resolution N(0,2^2) noise, bilinearly upsampled: what a flow network produces)")
+    ap.add_argument("--warp-variant", type=int, default=0, help="debug hook 3: 1 = force direct warp kernels, 2 = force window kernels")
     args = ap.parse_args()
     from arflow_b200 import _lib
     from arflow_b200.correlation import corr_out_dims
     lib = _lib.load()
     lib.arf_debug_set(1, args.variant)
     lib.arf_debug_set(2, args.probe)
+    lib.arf_debug_set(3, args.warp_variant)
     hbm, src = peaks()
     rows = []
 
@@ -110,23 +115,29 @@ def main():
             px = B * H * W
             a = (B, C, H, W, H, W, float(W - 1), float(H - 1), 0, 0, 0, 1)
 
-            def mk(kind):
-                def make():
-                    x = torch.randn(B, C, H, W, device="cuda")
-                    fl = torch.randn(B, 2, H, W, device="cuda") * 2
-                    y = torch.empty_like(x)
-                    gy = torch.randn_like(x)
-                    gx, gf = torch.empty_like(x), torch.empty_like(fl)
-                    if kind == "fwd":
-                        return lambda: lib.arf_warp_fwd(x.data_ptr(), fl.data_ptr(), y.data_ptr(), *a, cs())
-                    if kind == "bwd":
-                        return lambda: lib.arf_warp_bwd(x.data_ptr(), fl.data_ptr(), gy.data_ptr(), gx.data_ptr(),
-                                                        gf.data_ptr(), *a, cs())
-                    return lambda: lib.arf_warp_bwd(x.data_ptr(), fl.data_ptr(), gy.data_ptr(), None, gf.data_ptr(), *a, cs())
-                return make
-            report("warp_fwd", (B, C, H, W), px * (8 * C + 8), px * C * 8, *time_graph(mk("fwd"), px * (8 * C + 8)))
-            report("warp_bwd", (B, C, H, W), px * (12 * C + 16), px * C * 16, *time_graph(mk("bwd"), px * (12 * C + 16)))
-            report("warp_bwdF", (B, C, H, W), px * (8 * C + 16), px * C * 16, *time_graph(mk("bwdF"), px * (8 * C + 16)))
+            for flow_kind in (["iid", "smooth"] if args.flow == "both" else [args.flow]):
+                def mk(kind):
+                    def make():
+                        x = torch.randn(B, C, H, W, device="cuda")
+                        if flow_kind == "iid" or H < 16 or W < 16:
+                            fl = torch.randn(B, 2, H, W, device="cuda") * 2
+                        else:
+                            fl = torch.nn.functional.interpolate(torch.randn(B, 2, H // 8, W // 8, device="cuda") * 2,
+                                                                 size=(H, W), mode="bilinear").contiguous()
+                        y = torch.empty_like(x)
+                        gy = torch.randn_like(x)
+                        gx, gf = torch.empty_like(x), torch.empty_like(fl)
+                        if kind == "fwd":
+                            return lambda: lib.arf_warp_fwd(x.data_ptr(), fl.data_ptr(), y.data_ptr(), *a, cs())
+                        if kind == "bwd":
+                            return lambda: lib.arf_warp_bwd(x.data_ptr(), fl.data_ptr(), gy.data_ptr(), gx.data_ptr(),
+                                                            gf.data_ptr(), *a, cs())
+                        return lambda: lib.arf_warp_bwd(x.data_ptr(), fl.data_ptr(), gy.data_ptr(), None, gf.data_ptr(), *a, cs())
+                    return make
+                tag = "" if flow_kind == "iid" else "_smooth"
+                report("warp_fwd" + tag, (B, C, H, W), px * (8 * C + 8), px * C * 8, *time_graph(mk("fwd"), px * (8 * C + 8)))
+                report("warp_bwd" + tag, (B, C, H, W), px * (12 * C + 16), px * C * 16, *time_graph(mk("bwd"), px * (12 * C + 16)))
+                report("warp_bwdF" + tag, (B, C, H, W), px * (8 * C + 16), px * C * 16, *time_graph(mk("bwdF"), px * (8 * C + 16)))
     if args.what in ("census", "all"):
         cshapes = shapes if args.shapes else [(8, 3, 384, 512), (32, 3, 448, 1024)]
         for (B, C, H, W) in cshapes:
