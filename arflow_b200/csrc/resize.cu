@@ -21,72 +21,84 @@ __device__ __forceinline__ void src_index(int dst, float r, int in_size, int& i0
     l0 = 1.f - l1;
 }
 
-__global__ void resize_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, ResizeGeom g) {
-    long long total = (long long)g.N * g.Ho * g.Wo;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        int ox = idx % g.Wo;
-        long long t = idx / g.Wo;
-        int oy = t % g.Ho;
-        long long n = t / g.Ho;
-        int y0, y1, x0, x1;
-        float hy0, hy1, wx0, wx1;
-        src_index(oy, g.rh, g.Hi, y0, y1, hy0, hy1);
-        src_index(ox, g.rw, g.Wi, x0, x1, wx0, wx1);
-        const float* p = in + n * (long long)g.Hi * g.Wi;
-        float v = hy0 * (wx0 * __ldg(p + (size_t)y0 * g.Wi + x0) + wx1 * __ldg(p + (size_t)y0 * g.Wi + x1)) +
-                  hy1 * (wx0 * __ldg(p + (size_t)y1 * g.Wi + x0) + wx1 * __ldg(p + (size_t)y1 * g.Wi + x1));
-        out[idx] = v * g.mul;
+// grid = (pixel blocks of one plane, planes): 32-bit index math only (a 64-bit div/mod per pixel used to cost more
+// than the four taps)
+__global__ void __launch_bounds__(256) resize_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, ResizeGeom g) {
+    const unsigned npix = (unsigned)g.Ho * (unsigned)g.Wo;
+    for (unsigned n = blockIdx.y; n < (unsigned)g.N; n += gridDim.y) {
+        const float* p = in + (size_t)n * g.Hi * g.Wi;
+        float* q = out + (size_t)n * npix;
+        for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < npix; idx += gridDim.x * blockDim.x) {
+            const unsigned oy = idx / (unsigned)g.Wo, ox = idx - oy * (unsigned)g.Wo;
+            int y0, y1, x0, x1;
+            float hy0, hy1, wx0, wx1;
+            src_index((int)oy, g.rh, g.Hi, y0, y1, hy0, hy1);
+            src_index((int)ox, g.rw, g.Wi, x0, x1, wx0, wx1);
+            const float* r0 = p + (size_t)y0 * g.Wi;
+            const float* r1 = p + (size_t)y1 * g.Wi;
+            float v = hy0 * (wx0 * __ldg(r0 + x0) + wx1 * __ldg(r0 + x1)) + hy1 * (wx0 * __ldg(r1 + x0) + wx1 * __ldg(r1 + x1));
+            q[idx] = v * g.mul;
+        }
     }
 }
 
 // Gather-form backward: each input pixel sums the weights with which the output pixels of its
 // neighbourhood referenced it (deterministic, no atomics).
-__global__ void resize_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, ResizeGeom g) {
-    long long total = (long long)g.N * g.Hi * g.Wi;
+__global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, ResizeGeom g) {
+    const unsigned npix = (unsigned)g.Hi * (unsigned)g.Wi;
     // output rows whose taps can touch input row iy: source coordinate in (iy-1, iy+1)
     const float inv_rh = 1.f / g.rh, inv_rw = 1.f / g.rw;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        int ix = idx % g.Wi;
-        long long t = idx / g.Wi;
-        int iy = t % g.Hi;
-        long long n = t / g.Hi;
-        // exact range is [ceil(lo), ceil(hi) - 1]; floor/ceil leave one candidate of slack on each side against
-        // rounding, candidates that do not reference the pixel get weight 0 below
-        int oy_lo = max(0, (int)floorf(((float)iy - 0.5f) * inv_rh - 0.5f));
-        int oy_hi = min(g.Ho - 1, (int)ceilf(((float)iy + 1.5f) * inv_rh - 0.5f));
-        int ox_lo = max(0, (int)floorf(((float)ix - 0.5f) * inv_rw - 0.5f));
-        int ox_hi = min(g.Wo - 1, (int)ceilf(((float)ix + 1.5f) * inv_rw - 0.5f));
-        if (iy == 0) oy_lo = 0;            // rows clamped at the top edge all read row 0
-        if (ix == 0) ox_lo = 0;
-        if (iy == g.Hi - 1) oy_hi = g.Ho - 1;
-        if (ix == g.Wi - 1) ox_hi = g.Wo - 1;
-        const float* go = gout + n * (long long)g.Ho * g.Wo;
-        float acc = 0.f;
-        for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-            int y0, y1;
-            float hy0, hy1;
-            src_index(oy, g.rh, g.Hi, y0, y1, hy0, hy1);
-            float wy = (y0 == iy ? hy0 : 0.f) + (y1 == iy ? hy1 : 0.f);
-            if (wy == 0.f) continue;
-            float row = 0.f;
-            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-                int x0, x1;
-                float wx0, wx1;
-                src_index(ox, g.rw, g.Wi, x0, x1, wx0, wx1);
-                float wx = (x0 == ix ? wx0 : 0.f) + (x1 == ix ? wx1 : 0.f);
-                if (wx != 0.f) row = fmaf(wx, __ldg(go + (size_t)oy * g.Wo + ox), row);
+    for (unsigned n = blockIdx.y; n < (unsigned)g.N; n += gridDim.y) {
+        const float* go = gout + (size_t)n * g.Ho * g.Wo;
+        float* gi = gin + (size_t)n * npix;
+        for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < npix; idx += gridDim.x * blockDim.x) {
+            const int iy = (int)(idx / (unsigned)g.Wi), ix = (int)(idx - (unsigned)iy * (unsigned)g.Wi);
+            // exact range is [ceil(lo), ceil(hi) - 1]; floor/ceil leave one candidate of slack on each side against
+            // rounding, candidates that do not reference the pixel get weight 0 below
+            int oy_lo = max(0, (int)floorf(((float)iy - 0.5f) * inv_rh - 0.5f));
+            int oy_hi = min(g.Ho - 1, (int)ceilf(((float)iy + 1.5f) * inv_rh - 0.5f));
+            int ox_lo = max(0, (int)floorf(((float)ix - 0.5f) * inv_rw - 0.5f));
+            int ox_hi = min(g.Wo - 1, (int)ceilf(((float)ix + 1.5f) * inv_rw - 0.5f));
+            if (iy == 0) oy_lo = 0;            // rows clamped at the top edge all read row 0
+            if (ix == 0) ox_lo = 0;
+            if (iy == g.Hi - 1) oy_hi = g.Ho - 1;
+            if (ix == g.Wi - 1) ox_hi = g.Wo - 1;
+            float acc = 0.f;
+            for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+                int y0, y1;
+                float hy0, hy1;
+                src_index(oy, g.rh, g.Hi, y0, y1, hy0, hy1);
+                float wy = (y0 == iy ? hy0 : 0.f) + (y1 == iy ? hy1 : 0.f);
+                if (wy == 0.f) continue;
+                float row = 0.f;
+                for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                    int x0, x1;
+                    float wx0, wx1;
+                    src_index(ox, g.rw, g.Wi, x0, x1, wx0, wx1);
+                    float wx = (x0 == ix ? wx0 : 0.f) + (x1 == ix ? wx1 : 0.f);
+                    if (wx != 0.f) row = fmaf(wx, __ldg(go + (size_t)oy * g.Wo + ox), row);
+                }
+                acc = fmaf(wy, row, acc);
             }
-            acc = fmaf(wy, row, acc);
+            gi[idx] = acc * g.mul;
         }
-        gin[idx] = acc * g.mul;
     }
+}
+
+// grid for the two kernels: x covers one plane, y the planes (capped; both loops are strided)
+static inline dim3 resize_grid(long long pix_per_plane, long long planes) {
+    long long bx = (pix_per_plane + 255) / 256;
+    if (bx > 4096) bx = 4096;
+    long long by = planes < 65535 ? planes : 65535;
+    const long long cap = 16LL * ARF_NUM_SMS;
+    if (bx * by > cap) by = cap / bx > 0 ? cap / bx : 1;
+    return dim3((unsigned)bx, (unsigned)by);
 }
 
 int make_geom(ResizeGeom& g, long long N, int Hi, int Wi, int Ho, int Wo, float rh, float rw, float mul) {
     if (N <= 0 || N > 0x7fffffffLL || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0 || !(rh > 0.f) || !(rw > 0.f))
         return ARF_EINVAL;
+    if ((long long)Hi * Wi > 0x7fffffffLL || (long long)Ho * Wo > 0x7fffffffLL) return ARF_EINVAL;
     g.N = (int)N; g.Hi = Hi; g.Wi = Wi; g.Ho = Ho; g.Wo = Wo; g.rh = rh; g.rw = rw; g.mul = mul;
     return ARF_OK;
 }
@@ -99,8 +111,7 @@ extern "C" int arf_resize_bilinear_fwd(const float* in, float* out, long long pl
     ResizeGeom g;
     int rc = make_geom(g, planes, Hi, Wi, Ho, Wo, rh, rw, mul);
     if (rc) return rc;
-    long long total = planes * Ho * Wo;
-    resize_fwd_kernel<<<arf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, g);
+    resize_fwd_kernel<<<resize_grid((long long)Ho * Wo, planes), 256, 0, (cudaStream_t)stream>>>(in, out, g);
     ARF_CHECK_LAUNCH();
     return ARF_OK;
 }
@@ -111,8 +122,7 @@ extern "C" int arf_resize_bilinear_bwd(const float* gout, float* gin, long long 
     ResizeGeom g;
     int rc = make_geom(g, planes, Hi, Wi, Ho, Wo, rh, rw, mul);
     if (rc) return rc;
-    long long total = planes * Hi * Wi;
-    resize_bwd_kernel<<<arf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(gout, gin, g);
+    resize_bwd_kernel<<<resize_grid((long long)Hi * Wi, planes), 256, 0, (cudaStream_t)stream>>>(gout, gin, g);
     ARF_CHECK_LAUNCH();
     return ARF_OK;
 }

@@ -192,9 +192,11 @@ class PWCFlow(nn.Module):
                 x_in = torch.cat([context_up, flow_up, cost_volume, features1], dim=1)
             flow_layers = self._flow_layers[level]
             x_out = None
-            for layer in list(flow_layers)[:-1]:
+            dense = list(flow_layers)[:-1]
+            for i, layer in enumerate(dense):
                 x_out = layer(x_in)
-                x_in = torch.cat([x_in, x_out], dim=1)
+                if i + 1 < len(dense):   # the reference also concatenates after the last layer; that tensor is never read
+                    x_in = torch.cat([x_in, x_out], dim=1)
             context = x_out
             flow = flow_layers[-1](context)
 
