@@ -495,8 +495,20 @@ int g_probe = 0;         // test hook: see corr_fwd_md4
 int g_variant = 0;       // test hook: kernel variant selection while tuning
 int g_force_no_tma = 0;  // test hook: exercise the cp.async producer on TMA-capable shapes
 
-inline bool is_fast(const CorrGeom& g) {
+// The tiled kernels carry a fixed pipeline latency (forward ~11 us, backward ~35 us for any small problem) and, for
+// tensors TMA cannot describe (W % 4 != 0), a single-warp cp.async producer.  Measured with tools/microbench.py
+// (variant 5 = force literal, 6 = force tiled): the literal forward wins up to ~1000 output pixels (1x192x6x10:
+// 13 vs 277 us, 1x96x24x40: 12 vs 25 us; 16x32x12x16: 14 vs 12 us), the literal backward only for tiny non-TMA
+// shapes (1x192x6x10: 98 vs 342 us; 1x128x12x20: 99 vs 34 us).
+inline bool is_md4(const CorrGeom& g) {
     return g.ks == 1 && g.s1 == 1 && g.s2 == 1 && g.md == kMD && g.pad == kMD;
+}
+inline bool is_fast(const CorrGeom& g, bool bwd) {
+    if (!is_md4(g) || g_variant == 5) return false;
+    if (g_variant == 6) return true;
+    const long long px = (long long)g.B * g.H * g.W;
+    if (bwd) return !(g.W % 4 != 0 && px <= 512);
+    return px > 1024;
 }
 
 }  // namespace
@@ -529,7 +541,7 @@ extern "C" int arf_corr_fwd(const float* f1, const float* f2, float* out, int B,
     int rc = make_geom(g, B, C, H, W, pad, ks, md, s1, s2);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (is_fast(g)) {
+    if (is_fast(g, false)) {
         const int rg = (g_variant == 3 || g_variant == 4) ? 2 : 1;
         const int tiles_x = arf_cdiv(W, kTW), tiles_y = arf_cdiv(H, kTH * rg);
         const long long ntiles = (long long)tiles_x * tiles_y * B;
@@ -578,7 +590,7 @@ extern "C" int arf_corr_bwd(const float* f1, const float* f2, const float* gout,
     int rc = make_geom(g, B, C, H, W, pad, ks, md, s1, s2);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (is_fast(g)) {
+    if (is_fast(g, true)) {
         if (g1) {
             rc = launch_bwd_md4<false>(f2, gout, g1, B, C, H, W, !g_force_no_tma, st);
             if (rc) return rc;

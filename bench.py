@@ -129,6 +129,36 @@ def alg_bytes(name, a):
     return 0
 
 
+FP32_FMA_TFLOPS = 71.3   # tools/fma_peak.cu on this pool's B200 (1965 MHz), FFMA with 2 register operands
+MUFU_GOPS = 4544.0       # same tool, MUFU.RSQ
+
+
+def alg_work(name, a):
+    """(shape label, fp32 flops, MUFU ops) of one C-ABI call - the compute-side roofline numerators."""
+    if name == "arf_corr_fwd":
+        B, C, Hh, Ww = a[3:7]
+        return "B%d C%d %dx%d" % (B, C, Hh, Ww), B * Hh * Ww * C * 162, 0
+    if name == "arf_corr_bwd":
+        B, C, Hh, Ww = a[5:9]
+        return "B%d C%d %dx%d" % (B, C, Hh, Ww), B * Hh * Ww * C * 324, 0
+    if name == "arf_warp_fwd":
+        B, C, _, _, Ho, Wo = a[3:9]
+        return "B%d C%d %dx%d" % (B, C, Ho, Wo), B * Ho * Wo * C * 8, 0
+    if name == "arf_warp_bwd":
+        B, C, _, _, Ho, Wo = a[5:11]
+        return "B%d C%d %dx%d%s" % (B, C, Ho, Wo, "" if a[3] else " flow-grad only"), B * Ho * Wo * C * 16, 0
+    if name == "arf_census_fwd":
+        B, Hh, Ww, patch = a[6:10]
+        return "B%d %dx%d p%d" % (B, Hh, Ww, patch), B * Hh * Ww * 13 * (patch * patch - 1), B * Hh * Ww * 3 * (patch * patch - 1)
+    if name == "arf_census_bwd":
+        B, Hh, Ww, patch = a[9:13]
+        return "B%d %dx%d p%d" % (B, Hh, Ww, patch), B * Hh * Ww * 22 * (patch * patch - 1), B * Hh * Ww * 3 * (patch * patch - 1)
+    if name in ("arf_resize_bilinear_fwd", "arf_resize_bilinear_bwd"):
+        n, Hi, Wi, Ho, Wo = a[2:7]
+        return "N%d %dx%d->%dx%d" % (n, Hi, Wi, Ho, Wo), 0, 0
+    return "", 0, 0
+
+
 # ----------------------------------------------------------------------------- reference arm --
 def run_cpu_reference(steps, warmup, batch):
     """The reference's path on the host CPU cores (oracle port; the Python reference cannot travel to the
@@ -247,11 +277,30 @@ def main_b200(args):
     last = [float(v) for v in out.tolist()]
 
     # ---- end to end: pinned host -> device every step, loss read back every step ----
+    # Like a data loader would, the copy of batch i+1 is issued on a copy stream while step i computes; every batch
+    # still crosses PCIe inside the timed region and every step's loss is read back to the host before the next one.
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [torch.empty_like(devb[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def issue_copy(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])       # the step that last read this buffer has finished
+            bufs[i % 2].copy_(host[i % n_host], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    for ev in consumed:
+        ev.record()
     barrier()
     t0 = time.perf_counter()
+    issue_copy(0)
     for i in range(args.steps):
-        x = host[i % n_host].to(dev, non_blocking=True)
-        o = step(x)
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        o = step(bufs[i % 2])
+        consumed[i % 2].record()
+        if i + 1 < args.steps:
+            issue_copy(i + 1)
         _ = o[0].item()
     torch.cuda.synchronize()
     t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
@@ -271,6 +320,7 @@ def main_b200(args):
             for i in range(n_prof):
                 eager(devb[i % n_host])
             rec = _lib.profile_stop()
+            per_shape = {}
             for name, a, dt_ms in rec:
                 if name.endswith(("_out_dims", "_num_partials")):
                     continue                       # host-only helpers, no launch
@@ -278,20 +328,43 @@ def main_b200(args):
                 k["calls"] += 1
                 k["ms"] += dt_ms
                 k["bytes"] += alg_bytes(name, a)
+                label, flops, mufu = alg_work(name, a)
+                q = per_shape.setdefault((name, label), {"calls": 0, "ms": 0.0, "bytes": 0, "flops": 0, "mufu": 0})
+                q["calls"] += 1
+                q["ms"] += dt_ms
+                q["bytes"] += alg_bytes(name, a)
+                q["flops"] += flops
+                q["mufu"] += mufu
             hbm, how = measured_peaks()
-            top = max(kernels.items(), key=lambda kv: kv[1]["ms"])
-            name, k = top
+            # dominant = the (entry point, problem shape) with the most device time per step
+            (name, label), k = max(per_shape.items(), key=lambda kv: kv[1]["ms"])
             ach = k["bytes"] / (k["ms"] * 1e-3) / 1e9
-            roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                    "traffic": None, "peak_source": how,
+            roof = {"kernel": "%s [%s]" % (name, label), "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                    "frac": ach / hbm, "traffic": None, "peak_source": how,
                     "avg_launch_us": 1e3 * k["ms"] / k["calls"], "bytes_per_launch": k["bytes"] / k["calls"],
                     "step_share": k["ms"] / n_prof / (ms_total / args.steps),
-                    "note": "algorithmic bytes / CUDA-event time of the C-ABI call, in situ (L2-warm, inside the step)"}
+                    "fp32_tflops": k["flops"] / (k["ms"] * 1e-3) / 1e12,
+                    "fp32_frac": k["flops"] / (k["ms"] * 1e-3) / 1e12 / FP32_FMA_TFLOPS,
+                    "mufu_frac": k["mufu"] / (k["ms"] * 1e-3) / 1e9 / MUFU_GOPS,
+                    "note": "algorithmic bytes / CUDA-event time of the C-ABI call, in situ (L2-warm, inside an eager step; "
+                            "a C-ABI call may launch two kernels, e.g. the two correlation gradients). fp32_frac / "
+                            "mufu_frac: the same call against the measured FP32-FMA (%.1f TFLOP/s) and MUFU (%.0f Gop/s) "
+                            "peaks - the binding roof for the correlation gradients and the census kernels. "
+                            "L2-cold numbers at the sweep sizes: profiles/" % (FP32_FMA_TFLOPS, MUFU_GOPS)}
             for name, k in kernels.items():
                 k["us_per_step"] = 1e3 * k["ms"] / n_prof
                 k["alg_GBps"] = k["bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else None
                 k["calls_per_step"] = k["calls"] / n_prof
                 del k["ms"], k["bytes"], k["calls"]
+            shapes = []
+            for (name, label), q in sorted(per_shape.items(), key=lambda kv: -kv[1]["ms"])[:12]:
+                sec = q["ms"] * 1e-3
+                shapes.append({"call": "%s [%s]" % (name, label), "us_per_launch": 1e3 * q["ms"] / q["calls"],
+                               "launches_per_step": q["calls"] / n_prof,
+                               "hbm_frac": q["bytes"] / sec / 1e9 / hbm,
+                               "fp32_frac": q["flops"] / sec / 1e12 / FP32_FMA_TFLOPS,
+                               "mufu_frac": q["mufu"] / sec / 1e9 / MUFU_GOPS})
+            kernels["_by_shape"] = shapes
 
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None

@@ -259,6 +259,34 @@ def main():
                                    "keys": np.asarray(list(net.state_dict().keys()))})
 
 
+def prob_model():
+    """PWCProbFlow (config 3's network): eval mode, PyTorch default init in construction order."""
+    from easydict import EasyDict
+    from models.uflow_prob_model import PWCProbFlow
+    for tag, cfg, seed in (("nondiag", EasyDict(out_channels=[2, 2, 30], inv_cov=False, n_pyramids=1, mixture_weights=False,
+                                                feature_norm=True, level_dropout=0.1), 321),
+                           ("diag2pyr", EasyDict(out_channels=[2, 2, 0], inv_cov=True, n_pyramids=2, mixture_weights=False,
+                                                 feature_norm=True, level_dropout=0.1), 322)):
+        torch.manual_seed(seed)
+        net = PWCProbFlow(cfg)
+        net.init_weights()          # a no-op in the reference (iterates (name, module) tuples)
+        net.eval()
+        gen = torch.Generator().manual_seed(seed + 1000)    # regenerated by the test
+        im1, im2 = torch.rand(1, 3, 192, 256, generator=gen), torch.rand(1, 3, 192, 256, generator=gen)
+        with torch.no_grad():
+            r = net(im1, im2, with_bk=True)
+        save("pwcprobflow_" + tag, (np.asarray(seed),),
+             {"fw2": r["flows_fw"][2].numpy(), "bw2": r["flows_bw"][2].numpy(),
+              "fw0_absmean": np.asarray(r["flows_fw"][0].abs().mean(dim=(0, 2, 3)).numpy()),
+              "fw4": r["flows_fw"][4].numpy(),
+              "n_params": np.asarray(sum(p.numel() for p in net.parameters())),
+              "keys": np.asarray(list(net.state_dict().keys()))})
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "probflow":
+        prob_model()
+    else:
+        main()
+        prob_model()
