@@ -89,6 +89,20 @@ __global__ void corr_bwd_literal(const float* __restrict__ other, const float* _
     }
 }
 
+// Packed FP32 FMA (FFMA2, sm_100): two IEEE fused multiply-adds per lane and instruction.  ptxas turns a pair
+// built from the same scalar into the broadcast operand form (R.F32), so no MOV is spent on packing.
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void f2_fma(unsigned long long& d, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+
 // ------------------------------------------------------------------ tiled forward, md=4 --
 constexpr int kTW = 32;            // tile width  (lane <-> x)
 constexpr int kTH = 8;             // tile height (rows per thread)
@@ -96,21 +110,21 @@ constexpr int kMD = 4;
 constexpr int kD = 2 * kMD + 1;    // 9
 constexpr int kHW = kTW + 2 * kMD; // 40 halo width
 constexpr int kHH = kTH + 2 * kMD; // 16 halo height
-constexpr int kCc = 8;             // channels per pipeline stage
+constexpr int kCcDefault = 8;      // channels per pipeline stage
 // kRG row groups of 8 rows share one CTA tile (and its f2 halo): consumer warp w <-> (row group w/9, dx = w%9 - 4)
-template <int kRG>
+template <int kRG, int kCc>
 struct __align__(128) FwdStageT {
-    float s1[kCc][kTH * kRG][kTW];             // f1 tile                    8 KB per row group
+    float s1[kCc][kTH * kRG][kTW];             // f1 tile                    8 KB per row group (8 channels)
     float s2[kCc][kTH * kRG + 2 * kMD][kHW];   // f2 tile with 4-px halo    20 KB (RG=1) / 30 KB (RG=2)
 };
-template <int kRG>
-constexpr size_t fwd_smem(int stages) { return stages * sizeof(FwdStageT<kRG>) + 2 * stages * sizeof(uint64_t); }
+template <int kRG, int kCc>
+constexpr size_t fwd_smem(int stages) { return stages * sizeof(FwdStageT<kRG, kCc>) + 2 * stages * sizeof(uint64_t); }
 
 // Persistent, warp-specialised: warp 9 streams (f1 tile, f2 halo tile) channel chunks through a
 // kStages-deep shared-memory ring (TMA with hardware zero fill when kTma, else zero-filling
 // cp.async), warps 0..8 consume.  The ring keeps running across tile boundaries, so the loads of
 // the next tile overlap the 72 output stores per thread of the current one.
-template <bool kTma, int kRG, int kStg, int kMinBlocks, int kUnroll>
+template <bool kTma, int kRG, int kStg, int kMinBlocks, int kUnroll, bool kF2 = false, int kCc = kCcDefault>
 __global__ void __launch_bounds__(32 * (kD * kRG + 1), kMinBlocks)
 corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
              const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ out,
@@ -121,7 +135,7 @@ corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ C
     constexpr int kConsumerWarps = kD * kRG;
     constexpr int kTileH = kTH * kRG;            // CTA tile height
     constexpr int kHaloH = kTileH + 2 * kMD;
-    using FwdStage = FwdStageT<kRG>;
+    using FwdStage = FwdStageT<kRG, kCc>;
     constexpr uint32_t kFwdStageBytes = sizeof(FwdStage);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FwdStage* stg = reinterpret_cast<FwdStage*>(smem_raw);
@@ -201,6 +215,17 @@ corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ C
         for (int r = 0; r < kTH; ++r)
 #pragma unroll
             for (int d = 0; d < kD; ++d) acc[r][d] = 0.f;
+        // kF2: rows (2m, 2m+1) share packed accumulators.  pk[m][e-1] = (acc[2m][e], acc[2m+1][e-1]) for e = 1..8:
+        // one FFMA2 with the natural pair (a[2m], a[2m+1]) and the BROADCAST scalar bb[2m+e] updates both;
+        // acc[2m][0] and acc[2m+1][8] stay scalar.  32 FFMA2 + 8 FFMA per channel instead of 72 FFMA, same
+        // rounding (each accumulator sees the same fused multiply-adds in the same order).
+        unsigned long long pk[kTH / 2][kD - 1];
+        if (kF2) {
+#pragma unroll
+            for (int m = 0; m < kTH / 2; ++m)
+#pragma unroll
+                for (int e = 0; e < kD - 1; ++e) pk[m][e] = 0ull;
+        }
 
         for (int ch = 0; ch < nchunks; ++ch, ++it) {
             const int s = it % kStages;
@@ -209,6 +234,23 @@ corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ C
             const FwdStage& S = stg[s];
             if (probe == 1 || probe == 3) {
                 acc[0][0] += S.s1[0][r0][lane] + S.s2[0][r0][lane + wdx];
+            } else if (kF2) {
+#pragma unroll kUnroll
+                for (int cc = 0; cc < kCc; ++cc) {
+                    float a[kTH], bb[kHH];
+#pragma unroll
+                    for (int r = 0; r < kTH; ++r) a[r] = S.s1[cc][r0 + r][lane];
+#pragma unroll
+                    for (int k = 0; k < kHH; ++k) bb[k] = S.s2[cc][r0 + k][lane + wdx];
+#pragma unroll
+                    for (int m = 0; m < kTH / 2; ++m) {
+                        const unsigned long long ap = f2_pack(a[2 * m], a[2 * m + 1]);
+                        acc[2 * m][0] = fmaf(a[2 * m], bb[2 * m], acc[2 * m][0]);
+#pragma unroll
+                        for (int e = 1; e < kD; ++e) f2_fma(pk[m][e - 1], ap, f2_pack(bb[2 * m + e], bb[2 * m + e]));
+                        acc[2 * m + 1][kD - 1] = fmaf(a[2 * m + 1], bb[2 * m + kD], acc[2 * m + 1][kD - 1]);
+                    }
+                }
             } else
 #pragma unroll kUnroll
             for (int cc = 0; cc < kCc; ++cc) {
@@ -224,6 +266,12 @@ corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ C
             }
             __syncwarp();
             if (lane == 0) arf::mbar_arrive(&empty[s]);
+        }
+        if (kF2) {
+#pragma unroll
+            for (int m = 0; m < kTH / 2; ++m)
+#pragma unroll
+                for (int e = 1; e < kD; ++e) f2_unpack(pk[m][e - 1], acc[2 * m][e], acc[2 * m + 1][e - 1]);
         }
 
         if (probe == 1 || probe == 2) {
@@ -254,12 +302,15 @@ corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ C
 }
 
 // Tuning record (B=64, C=32, 96x128; probes in corr_fwd_md4): memory side alone (TMA loads + 255 MB of row
-// stores) 82 us, pure TMA streaming 33 us, LDS+FFMA loop alone 131 us, whole kernel 152 us.  The loop is bound by
-// shared-memory bytes per FMA: two alternative register tilings that read operands with LDS.128 along x
-// (12 px x 9 dx per thread, 8-10 shared-memory instructions per 108 FFMA instead of 24 per 72) were built and
-// measured at 118-148 us for the loop — the same 1.7x of their shared-memory-byte bound (~74 B/clk/SM effective)
-// as this kernel — and were dropped.  Getting past it needs fewer shared bytes per FMA (bigger register tiles
-// than the 168-register cap of a 10-warp CTA allows) or the tensor pipe (3xTF32 split), see DESIGN.md.
+// stores) 82 us, pure TMA streaming 33 us, LDS+FFMA loop alone 131 us, whole kernel 152 us.  ncu: no unit is
+// saturated (shared-memory data pipe 50%, LSU 58%, FMA 46%, issue 69%); the loop is a latency/issue mix of 24 LDS
+// feeding 72 FMAs per channel and warp.  Tried and measured:
+//   * register tilings that read operands with LDS.128 along x (12 px x 9 dx per thread): 118-148 us for the loop;
+//   * packed FFMA2 (32 FFMA2 + 8 FFMA instead of 72 FFMA per channel, broadcast operand, no MOVs, identical bits):
+//     163 us with one channel in flight, 149 us with two (kUnroll = 2) - the default now, 2.5% over scalar;
+//   * 6 stages of 4 channels instead of 3 of 8: 153-157 us; two row groups per CTA (1 CTA/SM): slower.
+// Getting further needs fewer shared-memory operands per FMA than a 72-accumulator thread tile allows (bigger tiles
+// do not fit two CTAs per SM) or the tensor pipe, which cannot meet the 1e-5 parity bar.
 
 // ------------------------------------------------------------------ tiled backward, md=4 -
 // g1[c,y,x] = 1/C sum_{dy,dx} gO[(dy,dx),y,x]       * f2[c,y+dy,x+dx]           (kSecond = false, F = f2)
@@ -546,31 +597,33 @@ extern "C" int arf_corr_fwd(const float* f1, const float* f2, float* out, int B,
         const int tiles_x = arf_cdiv(W, kTW), tiles_y = arf_cdiv(H, kTH * rg);
         const long long ntiles = (long long)tiles_x * tiles_y * B;
         if (ntiles > 0x7fffffffLL) return ARF_EINVAL;
+        const int cc = kCcDefault;   // channels per stage
         CUtensorMap m1, m2;
         bool tma = !g_force_no_tma && arf::tma_ok_nchw(f1, W) && arf::tma_ok_nchw(f2, W) &&
-                   arf::make_map_nchw(&m1, f1, B, C, H, W, kTW, kTH * rg, kCc) &&
-                   arf::make_map_nchw(&m2, f2, B, C, H, W, kHW, kTH * rg + 2 * kMD, kCc);
+                   arf::make_map_nchw(&m1, f1, B, C, H, W, kTW, kTH * rg, cc) &&
+                   arf::make_map_nchw(&m2, f2, B, C, H, W, kHW, kTH * rg + 2 * kMD, cc);
         if (!tma) {
             memset(&m1, 0, sizeof(m1));
             memset(&m2, 0, sizeof(m2));
         }
         const float inv_c = 1.0f / (float)C;
-#define ARF_LAUNCH_FWD(TMA, RG, STG, MINB, UNR)                                                              \
-    do {                                                                                                     \
-        auto kern = corr_fwd_md4<TMA, RG, STG, MINB, UNR>;                                                   \
-        static bool attr = false;                                                                            \
-        if (!attr) {                                                                                         \
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<RG>(STG)); \
-            attr = true;                                                                                     \
-        }                                                                                                    \
-        const int grid = (int)(ntiles < (MINB) * ARF_NUM_SMS ? ntiles : (MINB) * ARF_NUM_SMS);               \
-        kern<<<grid, 32 * (kD * RG + 1), fwd_smem<RG>(STG), st>>>(m1, m2, f1, f2, out, B, C, H, W, tiles_x,  \
-                                                                  tiles_y, inv_c, g_probe);                  \
+#define ARF_LAUNCH_FWD(TMA, RG, STG, MINB, UNR, F2, CC)                                                          \
+    do {                                                                                                         \
+        auto kern = corr_fwd_md4<TMA, RG, STG, MINB, UNR, F2, CC>;                                               \
+        static bool attr = false;                                                                                \
+        if (!attr) {                                                                                             \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<RG, CC>(STG)); \
+            attr = true;                                                                                         \
+        }                                                                                                        \
+        const int grid = (int)(ntiles < (MINB) * ARF_NUM_SMS ? ntiles : (MINB) * ARF_NUM_SMS);                   \
+        kern<<<grid, 32 * (kD * RG + 1), fwd_smem<RG, CC>(STG), st>>>(m1, m2, f1, f2, out, B, C, H, W, tiles_x,  \
+                                                                      tiles_y, inv_c, g_probe);                  \
     } while (0)
-        if (!tma) ARF_LAUNCH_FWD(false, 1, 3, 2, 1);
-        else if (g_variant == 3) ARF_LAUNCH_FWD(true, 2, 4, 1, 1);
-        else if (g_variant == 4) ARF_LAUNCH_FWD(true, 2, 3, 1, 1);
-        else ARF_LAUNCH_FWD(true, 1, 3, 2, 1);
+        if (!tma) ARF_LAUNCH_FWD(false, 1, 3, 2, 1, false, 8);
+        else if (g_variant == 3) ARF_LAUNCH_FWD(true, 2, 4, 1, 1, false, 8);
+        else if (g_variant == 4) ARF_LAUNCH_FWD(true, 2, 3, 1, 1, false, 8);
+        else if (g_variant == 7) ARF_LAUNCH_FWD(true, 1, 3, 2, 1, false, 8);   // scalar FFMA loop (same bits)
+        else ARF_LAUNCH_FWD(true, 1, 3, 2, 2, true, 8);                        // FFMA2 loop, two channels in flight
 #undef ARF_LAUNCH_FWD
         ARF_CHECK_LAUNCH();
         return ARF_OK;
