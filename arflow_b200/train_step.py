@@ -26,7 +26,14 @@ import torch.distributed as dist
 
 class UFlowTrainStep:
     def __init__(self, model, loss_fn, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, use_graph=True, world_size=1,
-                 n_buckets=3):
+                 n_buckets=3, global_census_norm=False):
+        if global_census_norm and world_size > 1:
+            # batch-global census normaliser: one more collective inside the forward pass,
+            # which rules out the captured fwd+bwd graph on this pool
+            if use_graph:
+                raise ValueError("global_census_norm needs use_graph=False (NCCL cannot be captured on this pool)")
+            from . import uflow_utils
+            uflow_utils.set_census_normaliser_group(dist.group.WORLD)
         self.model = model
         self.loss_fn = loss_fn
         self.world_size = world_size

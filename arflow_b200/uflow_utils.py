@@ -184,6 +184,34 @@ class _CensusHammingFunction(torch.autograd.Function):
         return ga, gb, None, None
 
 
+# Data-parallel training shards the batch, but the reference normalises the masked census mean by the mask sum of
+# the WHOLE batch (uflow_utils.py:293).  With a process group registered here, the per-rank denominator is replaced
+# by world * (global denominator) so that the gradient average over ranks equals the single-process gradient:
+#   mean_r [ W * num_r / (sum_r den_r + 1e-6) ] = sum_r num_r / (sum_r den_r + 1e-6).
+# The mask is detached, so this is a forward-only 4-byte all-reduce.  It is a collective inside the step, so it
+# cannot be used under CUDA-graph capture on this pool (see train_step.py); the default (None) keeps the per-rank
+# normaliser.
+_census_group = None
+
+
+def set_census_normaliser_group(group, enabled=True):
+    """group: a torch.distributed process group (or dist.group.WORLD); enabled=False / group=None switches back."""
+    global _census_group
+    _census_group = group if enabled else None
+
+
+def globalise_census_sums(sums, group):
+    """sums = [num, den, num/(den+1e-6)] of this rank -> the same triple with the batch-global normaliser."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    den = sums[1:2].clone()
+    dist.all_reduce(den, group=group)
+    out = sums.clone()
+    out[1] = (den[0] + 1e-6) / world - 1e-6          # so that 1 / (out[1] + 1e-6) = world / (global den + 1e-6)
+    out[2] = sums[0] / (out[1] + 1e-6)
+    return out
+
+
 class _CensusLossFunction(torch.autograd.Function):
     """census_loss (uflow_utils.py:282-293) fused: transform, soft Hamming, robust penalty, border-zeroed
     mask and the batch-global masked mean, one pass forward and one pass backward."""
@@ -205,6 +233,8 @@ class _CensusLossFunction(torch.autograd.Function):
             _lib.call("arf_census_fwd", _lib.dev_ptr(im_a, "image_a"), _lib.dev_ptr(im_b, "image_b"),
                       _lib.dev_ptr(mask, "mask"), _lib.dev_ptr(ham), _lib.dev_ptr(partials), _lib.dev_ptr(sums),
                       B, H, W, patch, 1.0, float(eps), float(q), _lib.stream_ptr())
+        if _census_group is not None:
+            sums = globalise_census_sums(sums, _census_group)
         ctx.save_for_backward(im_a, im_b, mask, ham, sums)
         ctx.cfg = (patch, float(eps), float(q))
         return sums[2]

@@ -69,3 +69,29 @@ def test_two_rank_gradient_average(tmp_path, oracle):
         ref = p.grad if p.grad is not None else torch.zeros_like(p)
         worst = max(worst, float((r0["g2"][s0:e0].view_as(p) - ref).abs().max()))
     assert worst <= 1e-4 * scale, (worst, scale)
+
+
+def _norm_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    from arflow_b200.uflow_utils import globalise_census_sums
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    num, den = (3.0, 10.0) if rank == 0 else (5.0, 30.0)       # per-rank masked sums
+    sums = torch.tensor([num, den, num / (den + 1e-6)])
+    torch.save(globalise_census_sums(sums, dist.group.WORLD), os.path.join(out_dir, "norm%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_global_census_normaliser_two_ranks(tmp_path):
+    """with the batch-global denominator the AVERAGE of the per-rank losses (what the averaged
+    gradient all-reduce optimises) equals the single-process loss sum(num) / (sum(den) + 1e-6)."""
+    port = 29800 + os.getpid() % 200
+    mp.spawn(_norm_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    s0 = torch.load(os.path.join(tmp_path, "norm0.pt"))
+    s1 = torch.load(os.path.join(tmp_path, "norm1.pt"))
+    want = (3.0 + 5.0) / (10.0 + 30.0 + 1e-6)
+    assert abs(float(s0[2] + s1[2]) / 2 - want) < 1e-6
+    # the backward kernel divides by (sums[1] + 1e-6): that must be world / (global den + 1e-6)
+    assert abs(1.0 / (float(s0[1]) + 1e-6) - 2.0 / (40.0 + 1e-6)) < 1e-7
+    assert float(s0[0]) == 3.0 and float(s1[0]) == 5.0
