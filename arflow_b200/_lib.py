@@ -39,6 +39,9 @@ PROTOTYPES = {
     "arf_smooth_num_partials": [c_int] * 3,
     "arf_smooth_fwd": [_P] * 4 + [c_int] * 8 + [c_float] * 3 + [_P],
     "arf_smooth_bwd": [_P] * 4 + [c_int] * 8 + [c_float] * 3 + [_P],
+    "arf_bias_leaky_num_partials": [ctypes.c_longlong, c_int, ctypes.c_longlong],
+    "arf_bias_leaky_fwd": [_P, _P, ctypes.c_longlong, c_int, ctypes.c_longlong, c_float, _P],
+    "arf_bias_leaky_bwd": [_P, _P, _P, _P, _P, ctypes.c_longlong, c_int, ctypes.c_longlong, c_float, _P],
     "arf_stencil_mv_fwd": [_P, _P, _P] + [c_int] * 5 + [_P],
     "arf_stencil_mv_bwd": [_P] * 5 + [c_int] * 5 + [_P],
     "arf_trisolve": [_P] * 6 + [ctypes.c_longlong, c_int, c_int, c_int, _P],
@@ -48,7 +51,8 @@ PROTOTYPES = {
     "arf_resampler_fwd": [_P, _P, _P, ctypes.c_longlong, _P] + [c_int] * 4 + [ctypes.c_longlong, _P],
     "arf_resampler_bwd": [_P, _P, _P, ctypes.c_longlong, _P, _P, _P, _P, ctypes.c_longlong] + [c_int] * 4 + [ctypes.c_longlong, _P],
 }
-_RESTYPES = {"arf_error_string": ctypes.c_char_p, "arf_launch_count": ctypes.c_longlong}
+_RESTYPES = {"arf_error_string": ctypes.c_char_p, "arf_launch_count": ctypes.c_longlong,
+             "arf_bias_leaky_num_partials": ctypes.c_longlong}
 
 _lib = None
 

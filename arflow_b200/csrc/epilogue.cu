@@ -1,0 +1,128 @@
+// Fused bias + leaky-ReLU epilogue of the PWC decoder / pyramid convolutions, forward and backward.
+//
+// The convolutions themselves stay on cuDNN (out of scope).  What the reference spends around every
+// one of them is: an elementwise bias add, an elementwise leaky ReLU (models/uflow_model.py:134-135, 427-436),
+// and in the backward pass an elementwise leaky-ReLU gradient followed by a separate full-tensor reduction for
+// the bias gradient.  Here the forward is ONE in-place pass over the convolution output and the backward is ONE
+// pass that writes the pre-activation gradient and reduces the bias gradient on the fly (two-stage, fixed
+// summation order).  Pure streaming: 8 B/element forward, 12 B/element backward.
+//   y   = leaky(conv + bias)                      (slope > 0, so sign(y) = sign(conv + bias))
+//   g   = gy * (y > 0 ? 1 : slope)                (ATen leaky_relu_backward: x > 0 ? g : g * slope)
+//   db  = sum over batch and pixels of g
+#include "common.cuh"
+
+namespace {
+
+constexpr int kEThreads = 256;
+constexpr int kEChunk = 4096;      // elements of one (b, c) plane handled by one CTA
+
+__global__ void __launch_bounds__(kEThreads)
+bias_leaky_fwd_kernel(float* __restrict__ y, const float* __restrict__ bias, int C, long long HW, float slope, int vec) {
+    const long long plane = blockIdx.x;
+    const float bv = bias ? __ldg(bias + (int)(plane % C)) : 0.f;
+    float* p = y + plane * HW;
+    const long long lo = (long long)blockIdx.y * kEChunk;
+    const long long hi = lo + kEChunk < HW ? lo + kEChunk : HW;
+    if (vec) {
+        for (long long e = lo + 4 * threadIdx.x; e < hi; e += 4 * kEThreads) {
+            float4 v = *reinterpret_cast<float4*>(p + e);
+            v.x += bv; v.y += bv; v.z += bv; v.w += bv;
+            v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+            v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+            *reinterpret_cast<float4*>(p + e) = v;
+        }
+    } else {
+        for (long long e = lo + threadIdx.x; e < hi; e += kEThreads) {
+            float v = p[e] + bv;
+            p[e] = v > 0.f ? v : v * slope;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kEThreads)
+bias_leaky_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y, float* __restrict__ g,
+                      float* __restrict__ partials, long long HW, float slope, int vec) {
+    __shared__ float red[32];
+    const long long plane = blockIdx.x;
+    const float* pg = gy + plane * HW;
+    const float* py = y + plane * HW;
+    float* po = g + plane * HW;
+    const long long lo = (long long)blockIdx.y * kEChunk;
+    const long long hi = lo + kEChunk < HW ? lo + kEChunk : HW;
+    float acc = 0.f;
+    if (vec) {
+        for (long long e = lo + 4 * threadIdx.x; e < hi; e += 4 * kEThreads) {
+            const float4 a = *reinterpret_cast<const float4*>(pg + e);
+            const float4 b = *reinterpret_cast<const float4*>(py + e);
+            float4 o;
+            o.x = b.x > 0.f ? a.x : a.x * slope; o.y = b.y > 0.f ? a.y : a.y * slope;
+            o.z = b.z > 0.f ? a.z : a.z * slope; o.w = b.w > 0.f ? a.w : a.w * slope;
+            *reinterpret_cast<float4*>(po + e) = o;
+            acc += (o.x + o.y) + (o.z + o.w);
+        }
+    } else {
+        for (long long e = lo + threadIdx.x; e < hi; e += kEThreads) {
+            const float a = pg[e];
+            const float o = py[e] > 0.f ? a : a * slope;
+            po[e] = o;
+            acc += o;
+        }
+    }
+    if (partials) {
+        const float s = arf_block_sum(acc, red);
+        if (threadIdx.x == 0) partials[plane * gridDim.y + blockIdx.y] = s;
+    }
+}
+
+// dbias[c] = sum over b and chunks of partials[(b*C + c)*nchunks + chunk]; one warp per channel, fixed order
+__global__ void bias_grad_finalize_kernel(const float* __restrict__ partials, float* __restrict__ dbias, long long B, int C,
+                                          int nchunks) {
+    const int c = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    const int lane = threadIdx.x & 31;
+    const long long n = B * nchunks;
+    double acc = 0.0;
+    for (long long i = lane; i < n; i += 32) {
+        const long long b = i / nchunks, k = i - b * nchunks;
+        acc += (double)partials[(b * C + c) * nchunks + k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) dbias[c] = (float)acc;
+}
+
+inline int nchunks_of(long long HW) { return (int)((HW + kEChunk - 1) / kEChunk); }
+
+}  // namespace
+
+extern "C" long long arf_bias_leaky_num_partials(long long B, int C, long long HW) {
+    if (B <= 0 || C <= 0 || HW <= 0) return ARF_EINVAL;
+    return B * C * nchunks_of(HW);
+}
+
+extern "C" int arf_bias_leaky_fwd(float* y, const float* bias, long long B, int C, long long HW, float slope, void* stream) {
+    ARF_REQUIRE(y);
+    ARF_REQUIRE(B > 0 && C > 0 && HW > 0 && B * C <= 0x7fffffffLL && nchunks_of(HW) <= 65535);
+    const int vec = ((uintptr_t)y % 16 == 0) && (HW % 4 == 0);
+    dim3 grid((unsigned)(B * C), (unsigned)nchunks_of(HW));
+    bias_leaky_fwd_kernel<<<grid, kEThreads, 0, (cudaStream_t)stream>>>(y, bias, C, HW, slope, vec);
+    ARF_CHECK_LAUNCH();
+    return ARF_OK;
+}
+
+extern "C" int arf_bias_leaky_bwd(const float* gy, const float* y, float* g, float* partials, float* dbias, long long B,
+                                  int C, long long HW, float slope, void* stream) {
+    ARF_REQUIRE(gy && y && g);
+    ARF_REQUIRE(B > 0 && C > 0 && HW > 0 && B * C <= 0x7fffffffLL && nchunks_of(HW) <= 65535);
+    if (dbias) ARF_REQUIRE(partials != nullptr);
+    const int vec = ((uintptr_t)gy % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)g % 16 == 0) && (HW % 4 == 0);
+    dim3 grid((unsigned)(B * C), (unsigned)nchunks_of(HW));
+    cudaStream_t st = (cudaStream_t)stream;
+    bias_leaky_bwd_kernel<<<grid, kEThreads, 0, st>>>(gy, y, g, dbias ? partials : nullptr, HW, slope, vec);
+    ARF_CHECK_LAUNCH();
+    if (dbias) {
+        bias_grad_finalize_kernel<<<arf_cdiv(C, 8), 256, 0, st>>>(partials, dbias, B, C, nchunks_of(HW));
+        ARF_CHECK_LAUNCH();
+    }
+    return ARF_OK;
+}

@@ -15,6 +15,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as func
 
+from .fused_conv import conv_bias_leaky
+
 
 class _CudaOps:
     """The hot-path ops the network needs; the oracle provides a CPU twin for the baseline leg."""
@@ -91,7 +93,7 @@ class PWCFeaturePyramid(nn.Module):
         features = []
         for group in self._convs:
             for conv in group:
-                x = func.leaky_relu(conv(x), negative_slope=self._leaky_relu_alpha)
+                x = conv_bias_leaky(conv, x, self._leaky_relu_alpha)
             features.append(x)
         if split_features_by_sample:
             n = len(features[0])
@@ -194,7 +196,7 @@ class PWCFlow(nn.Module):
             x_out = None
             dense = list(flow_layers)[:-1]
             for i, layer in enumerate(dense):
-                x_out = layer(x_in)
+                x_out = conv_bias_leaky(layer[0], x_in, self._leaky_relu_alpha)   # layer = Sequential(Conv2d, LeakyReLU)
                 if i + 1 < len(dense):   # the reference also concatenates after the last layer; that tensor is never read
                     x_in = torch.cat([x_in, x_out], dim=1)
             context = x_out
@@ -211,8 +213,10 @@ class PWCFlow(nn.Module):
             flows.insert(0, flow)
 
         refinement = torch.cat([context, flow], dim=1)
-        for layer in self._refine_model:
-            refinement = layer(refinement)
+        refine = list(self._refine_model)          # conv, LeakyReLU, conv, LeakyReLU, ..., conv
+        for conv in refine[:-1:2]:
+            refinement = conv_bias_leaky(conv, refinement, self._leaky_relu_alpha)
+        refinement = refine[-1](refinement)
         keep = self._keep(refinement, groups)
         if keep is not None:
             refinement = refinement * keep

@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as func
 
+from .fused_conv import conv_bias_leaky
 from .uflow_model import PWCFeaturePyramid, _CudaOps, normalize_features
 
 
@@ -143,7 +144,7 @@ class PWCProbFlow(nn.Module):
             dense = list(self._flow_layers[level])[:-1]
             x_out = None
             for i, layer in enumerate(dense):
-                x_out = layer(x_in)
+                x_out = conv_bias_leaky(layer[0], x_in, self._leaky_relu_alpha)
                 if i + 1 < len(dense):
                     x_in = torch.cat([x_in, x_out], dim=1)
             context = x_out
@@ -164,8 +165,10 @@ class PWCProbFlow(nn.Module):
         if out.shape[1] < L + M + N:
             out = torch.cat([out, out.new_zeros(out.shape[0], L + M + N - out.shape[1], *out.shape[2:])], dim=1)
         refinement = torch.cat([context, out], dim=1)
-        for layer in self._refine_model:
-            refinement = layer(refinement)
+        refine = list(self._refine_model)          # conv, LeakyReLU, ..., conv
+        for conv in refine[:-1:2]:
+            refinement = conv_bias_leaky(conv, refinement, self._leaky_relu_alpha)
+        refinement = refine[-1](refinement)
         keep = self._keep(refinement, groups)
         if keep is not None:
             refinement = refinement * keep

@@ -161,6 +161,17 @@ int arf_smooth_bwd(const float* img, const float* flow, const float* gloss, floa
                    int order, int wstride, int woff, int penalty, float edge, float eps2, float final_scale,
                    void* stream);
 
+/* ---------------------------------------------------------------- conv epilogue -------- */
+/* Bias + leaky ReLU around the (cuDNN) convolutions of the PWC networks: nn.Conv2d(bias=True) followed by
+ * nn.LeakyReLU / func.leaky_relu (models/uflow_model.py:134-135, 427-436; uflow_prob_model.py:445-456).
+ * fwd, in place on the convolution output y (B,C,HW):  y = leaky(y + bias[c]); bias may be NULL.
+ * bwd, one pass:  g = gy * (y > 0 ? 1 : slope)  and  dbias[c] = sum_{b,hw} g  (dbias NULL: no reduction).
+ * partials: arf_bias_leaky_num_partials(B,C,HW) floats (two-stage, deterministic bias gradient). */
+long long arf_bias_leaky_num_partials(long long B, int C, long long HW);
+int arf_bias_leaky_fwd(float* y, const float* bias, long long B, int C, long long HW, float slope, void* stream);
+int arf_bias_leaky_bwd(const float* gy, const float* y, float* g, float* partials, float* dbias, long long B, int C,
+                       long long HW, float slope, void* stream);
+
 /* ---------------------------------------------------------------- stencil-triangular ---- */
 /* matrix_vector_product_general / _T_general (utils/triag_solve.py:29-43, 59-73).
  * A: (N, 2*(k+1)^2, H, W), tap t = i*(k+1)+j occupies channels 2t, 2t+1 (u, v); X, Y: (N,2,H,W).
