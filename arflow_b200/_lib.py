@@ -42,6 +42,11 @@ PROTOTYPES = {
     "arf_bias_leaky_num_partials": [ctypes.c_longlong, c_int, ctypes.c_longlong],
     "arf_bias_leaky_fwd": [_P, _P, ctypes.c_longlong, c_int, ctypes.c_longlong, c_float, _P],
     "arf_bias_leaky_bwd": [_P, _P, _P, _P, _P, ctypes.c_longlong, c_int, ctypes.c_longlong, c_float, _P],
+    "arf_bias_leaky_nhwc_num_partials": [ctypes.c_longlong, c_int],
+    "arf_bias_leaky_nhwc_fwd": [_P, _P, ctypes.c_longlong, c_int, c_float, _P],
+    "arf_bias_leaky_nhwc_bwd": [_P, _P, _P, _P, _P, ctypes.c_longlong, c_int, c_float, _P],
+    "arf_nhwc_pack": [_P, _P, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, c_int, c_int, _P],
+    "arf_nhwc_unpack": [_P, _P, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, c_int, c_int, _P],
     "arf_stencil_mv_fwd": [_P, _P, _P] + [c_int] * 5 + [_P],
     "arf_stencil_mv_bwd": [_P] * 5 + [c_int] * 5 + [_P],
     "arf_trisolve": [_P] * 6 + [ctypes.c_longlong, c_int, c_int, c_int, _P],
@@ -52,7 +57,7 @@ PROTOTYPES = {
     "arf_resampler_bwd": [_P, _P, _P, ctypes.c_longlong, _P, _P, _P, _P, ctypes.c_longlong] + [c_int] * 4 + [ctypes.c_longlong, _P],
 }
 _RESTYPES = {"arf_error_string": ctypes.c_char_p, "arf_launch_count": ctypes.c_longlong,
-             "arf_bias_leaky_num_partials": ctypes.c_longlong}
+             "arf_bias_leaky_num_partials": ctypes.c_longlong, "arf_bias_leaky_nhwc_num_partials": ctypes.c_longlong}
 
 _lib = None
 

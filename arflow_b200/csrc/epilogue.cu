@@ -93,6 +93,138 @@ __global__ void bias_grad_finalize_kernel(const float* __restrict__ partials, fl
 
 inline int nchunks_of(long long HW) { return (int)((HW + kEChunk - 1) / kEChunk); }
 
+// ---- NHWC (channels-last) variants: y is a (rows = N*H*W) x C row-major matrix --------------------------------
+constexpr int kERows = 64;        // rows of the matrix handled by one CTA of the backward
+
+__global__ void __launch_bounds__(kEThreads)
+bias_leaky_nhwc_fwd_kernel(float* __restrict__ y, const float* __restrict__ bias, long long total, int C, float slope, int vec) {
+    if (vec) {
+        for (long long e = 4 * (blockIdx.x * (long long)kEThreads + threadIdx.x); e < total; e += 4LL * gridDim.x * kEThreads) {
+            float4 v = *reinterpret_cast<float4*>(y + e);
+            if (bias) {
+                const float4 b = *reinterpret_cast<const float4*>(bias + (int)(e % C));
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+            v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+            *reinterpret_cast<float4*>(y + e) = v;
+        }
+    } else {
+        for (long long e = blockIdx.x * (long long)kEThreads + threadIdx.x; e < total; e += (long long)gridDim.x * kEThreads) {
+            float v = y[e] + (bias ? __ldg(bias + (int)(e % C)) : 0.f);
+            y[e] = v > 0.f ? v : v * slope;
+        }
+    }
+}
+
+// One CTA: kERows rows x all C columns.  Thread t owns column group (t % G) (4 columns when vec, else 1) and walks
+// rows t / G, t / G + 256 / G, ...; the per-thread column sums are reduced through shared memory, one partial row
+// of C sums per CTA.
+__global__ void __launch_bounds__(kEThreads)
+bias_leaky_nhwc_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y, float* __restrict__ g,
+                           float* __restrict__ partials, long long rows, int C, float slope, int vec) {
+    extern __shared__ float sacc[];          // kEThreads * 4 floats
+    const long long r0 = (long long)blockIdx.x * kERows;
+    const long long r1 = r0 + kERows < rows ? r0 + kERows : rows;
+    const int w = vec ? 4 : 1;
+    const int G = C / w;                     // column groups per row
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // a thread keeps ONE column group (t % G) for all its rows, so its sums stay in registers
+    const bool fixed = G <= kEThreads;
+    if (fixed) {
+        const int cg = threadIdx.x % G, rstep = kEThreads / G;      // threads >= rstep * G stay idle (G = 24: 240 of 256)
+        for (long long r = r0 + threadIdx.x / G; r < r1 && threadIdx.x < rstep * G; r += rstep) {
+            const long long e = r * C + (long long)cg * w;
+            if (vec) {
+                const float4 a = *reinterpret_cast<const float4*>(gy + e);
+                const float4 b = *reinterpret_cast<const float4*>(y + e);
+                float4 o;
+                o.x = b.x > 0.f ? a.x : a.x * slope; o.y = b.y > 0.f ? a.y : a.y * slope;
+                o.z = b.z > 0.f ? a.z : a.z * slope; o.w = b.w > 0.f ? a.w : a.w * slope;
+                *reinterpret_cast<float4*>(g + e) = o;
+                acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+            } else {
+                const float a = gy[e];
+                const float o = y[e] > 0.f ? a : a * slope;
+                g[e] = o;
+                acc.x += o;
+            }
+        }
+        if (partials) {
+            sacc[threadIdx.x * 4 + 0] = acc.x; sacc[threadIdx.x * 4 + 1] = acc.y;
+            sacc[threadIdx.x * 4 + 2] = acc.z; sacc[threadIdx.x * 4 + 3] = acc.w;
+            __syncthreads();
+            for (int c = threadIdx.x; c < C; c += kEThreads) {
+                const int cg2 = c / w, k = c - cg2 * w;
+                float s = 0.f;
+                for (int t = cg2; t < rstep * G; t += G) s += sacc[t * 4 + k];
+                partials[(long long)blockIdx.x * C + c] = s;
+            }
+        }
+    } else {
+        // generic widths (not used by the PWC networks): elementwise pass, then each thread sums whole columns
+        for (long long e = r0 * C + threadIdx.x; e < r1 * C; e += kEThreads) {
+            const float a = gy[e];
+            g[e] = y[e] > 0.f ? a : a * slope;
+        }
+        if (partials) {
+            __syncthreads();
+            for (int c = threadIdx.x; c < C; c += kEThreads) {
+                float s = 0.f;
+                for (long long r = r0; r < r1; ++r) s += g[r * C + c];
+                partials[(long long)blockIdx.x * C + c] = s;
+            }
+        }
+    }
+}
+
+// dbias[c] = sum over CTAs of partials[cta*C + c]; thread <-> channel (coalesced rows), fixed order
+__global__ void bias_grad_nhwc_finalize_kernel(const float* __restrict__ partials, float* __restrict__ dbias, long long nblk, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double acc = 0.0;
+    for (long long i = 0; i < nblk; ++i) acc += (double)partials[i * C + c];
+    dbias[c] = (float)acc;
+}
+
+}  // namespace
+
+extern "C" long long arf_bias_leaky_nhwc_num_partials(long long rows, int C) {
+    if (rows <= 0 || C <= 0) return ARF_EINVAL;
+    return ((rows + kERows - 1) / kERows) * C;
+}
+
+extern "C" int arf_bias_leaky_nhwc_fwd(float* y, const float* bias, long long rows, int C, float slope, void* stream) {
+    ARF_REQUIRE(y);
+    ARF_REQUIRE(rows > 0 && C > 0);
+    const int vec = ((uintptr_t)y % 16 == 0) && (C % 4 == 0) && (!bias || (uintptr_t)bias % 16 == 0);
+    const long long total = rows * C;
+    bias_leaky_nhwc_fwd_kernel<<<arf_grid_1d(vec ? total / 4 : total, kEThreads, 16), kEThreads, 0, (cudaStream_t)stream>>>(
+        y, bias, total, C, slope, vec);
+    ARF_CHECK_LAUNCH();
+    return ARF_OK;
+}
+
+extern "C" int arf_bias_leaky_nhwc_bwd(const float* gy, const float* y, float* g, float* partials, float* dbias,
+                                       long long rows, int C, float slope, void* stream) {
+    ARF_REQUIRE(gy && y && g);
+    ARF_REQUIRE(rows > 0 && C > 0);
+    if (dbias) ARF_REQUIRE(partials != nullptr);
+    const long long nblk = (rows + kERows - 1) / kERows;
+    if (nblk > 0x7fffffffLL) return ARF_EINVAL;
+    const int vec = ((uintptr_t)gy % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)g % 16 == 0) && (C % 4 == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    bias_leaky_nhwc_bwd_kernel<<<(unsigned)nblk, kEThreads, kEThreads * 4 * sizeof(float), st>>>(
+        gy, y, g, dbias ? partials : nullptr, rows, C, slope, vec);
+    ARF_CHECK_LAUNCH();
+    if (dbias) {
+        bias_grad_nhwc_finalize_kernel<<<arf_cdiv(C, 128), 128, 0, st>>>(partials, dbias, nblk, C);
+        ARF_CHECK_LAUNCH();
+    }
+    return ARF_OK;
+}
+
+namespace {
 }  // namespace
 
 extern "C" long long arf_bias_leaky_num_partials(long long B, int C, long long HW) {

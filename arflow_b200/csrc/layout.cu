@@ -1,0 +1,133 @@
+// Channel-concatenation into a packed NHWC tensor, and its inverse (the "decoder concat" of SURVEY §8f item 4).
+//
+// cuDNN's Blackwell convolution kernels are NHWC kernels: handed NCHW activations it transposes every input and
+// output itself (6.6 ms of a 24 ms chairs_uflow step, ncu launch list), and NHWC activations whose channel count is
+// not a multiple of 4 go through a padding copy.  The PWC decoder therefore keeps its dense-block activations as
+// packed NHWC tensors with the channel count rounded up to a multiple of 8; this file builds them:
+//   pack:   dst[n, p, c_off + c] = src part (either NHWC [n, p, c] or NCHW [n, c, p]);  pad channels are zeroed
+//   unpack: gsrc part            = gdst[n, p, c_off + c]                  (backward of pack, same two formats)
+// replacing torch.cat (models/uflow_model.py:189-205) and CatBackward.  NCHW parts (the cost volume and the flow
+// come from the NCHW hot-path kernels) go through a 32-pixel x 32-channel shared-memory transpose so that both the
+// reads (along pixels) and the writes (along channels) are coalesced.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kLThreads = 256;
+
+// NHWC part <-> NHWC destination slice: rows = N*HW pixels, part width Cs, destination width Cd, offset c_off.
+template <bool kPack>
+__global__ void __launch_bounds__(kLThreads)
+nhwc_part_kernel(float* __restrict__ dst, const float* __restrict__ src, long long rows, int Cs, int Cd, int c_off, int vec) {
+    // kPack:  dst[row*Cd + c_off + c] = src[row*Cs + c]     (src may be null: zero fill)
+    // !kPack: dst is the PART (width Cs), src the packed tensor (width Cd)
+    if (vec) {
+        const int q = Cs >> 2;
+        const long long total = rows * q;
+        for (long long e = blockIdx.x * (long long)kLThreads + threadIdx.x; e < total; e += (long long)gridDim.x * kLThreads) {
+            const long long row = e / q;
+            const int c = (int)(e - row * q) << 2;
+            if (kPack) {
+                float4 v = src ? *reinterpret_cast<const float4*>(src + row * Cs + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(dst + row * Cd + c_off + c) = v;
+            } else {
+                *reinterpret_cast<float4*>(dst + row * Cs + c) = *reinterpret_cast<const float4*>(src + row * Cd + c_off + c);
+            }
+        }
+    } else {
+        const long long total = rows * Cs;
+        for (long long e = blockIdx.x * (long long)kLThreads + threadIdx.x; e < total; e += (long long)gridDim.x * kLThreads) {
+            const long long row = e / Cs;
+            const int c = (int)(e - row * Cs);
+            if (kPack) dst[row * Cd + c_off + c] = src ? src[row * Cs + c] : 0.f;
+            else dst[row * Cs + c] = src[row * Cd + c_off + c];
+        }
+    }
+}
+
+// NCHW part [n][c][p] <-> packed NHWC [n][p][Cd] slice, through a 32 x 32 (+1) shared-memory tile.
+// grid = (pixel tiles, channel tiles, n), block = (32, 8).
+template <bool kPack>
+__global__ void __launch_bounds__(256)
+nchw_part_kernel(float* __restrict__ dst, const float* __restrict__ src, long long HW, int Cs, int Cd, int c_off) {
+    __shared__ float tile[32][33];
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const long long n = blockIdx.z;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    if (kPack) {
+        // read: lanes along pixels of one channel
+        const float* s = src + n * Cs * HW;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c0 + ty + 8 * k;
+            const long long p = p0 + tx;
+            tile[ty + 8 * k][tx] = (c < Cs && p < HW) ? __ldg(s + (long long)c * HW + p) : 0.f;
+        }
+        __syncthreads();
+        // write: lanes along channels of one pixel
+        float* d = dst + n * HW * Cd + c_off;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long p = p0 + ty + 8 * k;
+            const int c = c0 + tx;
+            if (c < Cs && p < HW) d[p * Cd + c] = tile[tx][ty + 8 * k];
+        }
+    } else {
+        // dst = NCHW part, src = packed NHWC
+        const float* s = src + n * HW * Cd + c_off;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long p = p0 + ty + 8 * k;
+            const int c = c0 + tx;
+            tile[ty + 8 * k][tx] = (c < Cs && p < HW) ? __ldg(s + p * Cd + c) : 0.f;
+        }
+        __syncthreads();
+        float* d = dst + n * Cs * HW;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c0 + ty + 8 * k;
+            const long long p = p0 + tx;
+            if (c < Cs && p < HW) d[(long long)c * HW + p] = tile[tx][ty + 8 * k];
+        }
+    }
+}
+
+template <bool kPack>
+int launch_part(float* dst, const float* src, long long N, long long HW, int Cs, int Cd, int c_off, int src_nhwc,
+                cudaStream_t st) {
+    if (N <= 0 || HW <= 0 || Cs <= 0 || Cd <= 0 || c_off < 0 || c_off + Cs > Cd) return ARF_EINVAL;
+    const float* part = kPack ? src : dst;       // the tensor that has the part's own layout
+    if (src_nhwc || (kPack && !src)) {
+        const float* packed = kPack ? dst : src;
+        const int vec = (Cs % 4 == 0) && (Cd % 4 == 0) && (c_off % 4 == 0) && ((uintptr_t)packed % 16 == 0) &&
+                        (!part || (uintptr_t)part % 16 == 0);
+        const long long work = N * HW * (vec ? Cs / 4 : Cs);
+        nhwc_part_kernel<kPack><<<arf_grid_1d(work, kLThreads, 16), kLThreads, 0, st>>>(dst, src, N * HW, Cs, Cd, c_off, vec);
+    } else {
+        if (N > 65535 || (Cs + 31) / 32 > 65535) return ARF_EINVAL;
+        dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((Cs + 31) / 32), (unsigned)N);
+        nchw_part_kernel<kPack><<<grid, dim3(32, 8), 0, st>>>(dst, src, HW, Cs, Cd, c_off);
+    }
+    return ARF_OK;
+}
+
+}  // namespace
+
+extern "C" int arf_nhwc_pack(float* dst, const float* src, long long N, long long HW, int Cs, int Cd, int c_off,
+                             int src_nhwc, void* stream) {
+    ARF_REQUIRE(dst);
+    int rc = launch_part<true>(dst, src, N, HW, Cs, Cd, c_off, src_nhwc, (cudaStream_t)stream);
+    if (rc) return rc;
+    ARF_CHECK_LAUNCH();
+    return ARF_OK;
+}
+
+extern "C" int arf_nhwc_unpack(float* part, const float* packed, long long N, long long HW, int Cs, int Cd, int c_off,
+                               int part_nhwc, void* stream) {
+    ARF_REQUIRE(part && packed);
+    int rc = launch_part<false>(part, packed, N, HW, Cs, Cd, c_off, part_nhwc, (cudaStream_t)stream);
+    if (rc) return rc;
+    ARF_CHECK_LAUNCH();
+    return ARF_OK;
+}

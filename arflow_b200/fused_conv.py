@@ -1,4 +1,4 @@
-"""Convolution + bias + leaky ReLU with a fused epilogue (arf_bias_leaky_fwd / _bwd).
+"""Convolution + bias + leaky ReLU with a fused epilogue, and the NHWC dense-block plumbing of the PWC decoders.
 
 The convolution itself is cuDNN (aten.convolution / aten.convolution_backward — out of scope).
 What is fused is everything the reference spends around it in `nn.Sequential(nn.Conv2d, nn.LeakyReLU)` and
@@ -6,11 +6,25 @@ What is fused is everything the reference spends around it in `nn.Sequential(nn.
 pass over the convolution output, and leaky-ReLU gradient + bias gradient become one pass in the backward
 (instead of an elementwise kernel plus a separate full-tensor reduction per layer).  Same fp32 arithmetic:
 y = leaky(conv + b);  g = gy * (y > 0 ? 1 : slope);  db = sum g.
+
+Layout.  cuDNN's sm_100 convolution kernels are NHWC kernels; fed NCHW activations they transpose every input and
+output themselves, and NHWC activations whose channel count is not a multiple of 4 take a padding copy.  With
+`nhwc_concat` the decoder builds its dense-block inputs directly as packed channels-last tensors whose channel
+count is a multiple of 8 (zero channels at the end of the first concat, matching zero columns inserted into the
+weights by `pad_in_channels`), so the convolutions run without any layout kernel.  Tensors keep their logical
+(B, C, H, W) shape; "NHWC" below means `memory_format=torch.channels_last` strides.
 """
 import torch
 import torch.nn.functional as func
 
 from . import _lib
+
+CL = torch.channels_last
+
+
+def is_nhwc(t):
+    """True for a channels-last dense 4-D tensor that is not also NCHW-contiguous (C == 1 or H*W == 1 are both)."""
+    return t.dim() == 4 and t.is_contiguous(memory_format=CL) and not t.is_contiguous()
 
 
 def _int_padding(conv):
@@ -27,44 +41,137 @@ def _int_padding(conv):
 class _ConvBiasLeaky(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride, padding, dilation, slope):
-        y = func.conv2d(x, weight, None, stride, padding, dilation).contiguous()
+        nhwc = is_nhwc(x)
+        y = func.conv2d(x, weight, None, stride, padding, dilation)
+        y = y.contiguous(memory_format=CL) if nhwc else y.contiguous()
         B, C, H, W = y.shape
+        bptr = _lib.dev_ptr(bias.contiguous(), "bias") if bias is not None else None
         with torch.cuda.device_of(y):
-            _lib.call("arf_bias_leaky_fwd", _lib.dev_ptr(y, "conv output"),
-                      _lib.dev_ptr(bias.contiguous(), "bias") if bias is not None else None,
-                      B, C, H * W, float(slope), _lib.stream_ptr())
+            if nhwc:
+                _lib.call("arf_bias_leaky_nhwc_fwd", y.data_ptr(), bptr, B * H * W, C, float(slope), _lib.stream_ptr())
+            else:
+                _lib.call("arf_bias_leaky_fwd", _lib.dev_ptr(y, "conv output"), bptr, B, C, H * W, float(slope),
+                          _lib.stream_ptr())
         ctx.save_for_backward(x, weight, y)
-        ctx.cfg = (list(stride), list(padding), list(dilation), float(slope), bias is not None)
+        ctx.cfg = (list(stride), list(padding), list(dilation), float(slope), bias is not None, nhwc)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, weight, y = ctx.saved_tensors
-        stride, padding, dilation, slope, has_bias = ctx.cfg
-        gy = gy.contiguous()
+        stride, padding, dilation, slope, has_bias, nhwc = ctx.cfg
+        gy = gy.contiguous(memory_format=CL) if nhwc else gy.contiguous()
         B, C, H, W = y.shape
         need_b = has_bias and ctx.needs_input_grad[2]
         lib = _lib.load()
         with torch.cuda.device_of(y):
-            g = torch.empty_like(y)
+            g = torch.empty_like(y)     # preserves the memory format
             db = torch.empty(C, dtype=y.dtype, device=y.device) if need_b else None
-            part = (torch.empty(lib.arf_bias_leaky_num_partials(B, C, H * W), dtype=y.dtype, device=y.device)
-                    if need_b else None)
-            _lib.call("arf_bias_leaky_bwd", _lib.dev_ptr(gy, "grad"), _lib.dev_ptr(y), _lib.dev_ptr(g),
-                      _lib.dev_ptr(part, allow_none=True), _lib.dev_ptr(db, allow_none=True),
-                      B, C, H * W, slope, _lib.stream_ptr())
+            if nhwc:
+                part = (torch.empty(lib.arf_bias_leaky_nhwc_num_partials(B * H * W, C), dtype=y.dtype, device=y.device)
+                        if need_b else None)
+                _lib.call("arf_bias_leaky_nhwc_bwd", gy.data_ptr(), y.data_ptr(), g.data_ptr(),
+                          part.data_ptr() if need_b else None, db.data_ptr() if need_b else None,
+                          B * H * W, C, slope, _lib.stream_ptr())
+            else:
+                part = (torch.empty(lib.arf_bias_leaky_num_partials(B, C, H * W), dtype=y.dtype, device=y.device)
+                        if need_b else None)
+                _lib.call("arf_bias_leaky_bwd", _lib.dev_ptr(gy, "grad"), _lib.dev_ptr(y), _lib.dev_ptr(g),
+                          _lib.dev_ptr(part, allow_none=True), _lib.dev_ptr(db, allow_none=True),
+                          B, C, H * W, slope, _lib.stream_ptr())
         gx, gw, _ = torch.ops.aten.convolution_backward(
             g, x, weight, None, stride, padding, dilation, False, [0, 0], 1,
             [bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1]), False])
         return gx, gw, db, None, None, None, None
 
 
-def conv_bias_leaky(conv, x, negative_slope):
-    """leaky_relu(conv(x)) for an nn.Conv2d `conv` (groups 1).  CUDA tensors take the fused path; a CPU tensor means
-    the caller is the oracle-backed CPU twin of the network (tests, bench.py's cpu_baseline) and gets plain torch."""
+def conv_bias_leaky(conv, x, negative_slope, weight=None):
+    """leaky_relu(conv(x)) for an nn.Conv2d `conv` (groups 1); `weight` overrides conv.weight (padded / channels-last
+    copy).  CUDA tensors take the fused path; a CPU tensor means the caller is the oracle-backed CPU twin of the
+    network (tests, bench.py's cpu_baseline) and gets plain torch."""
     if not x.is_cuda:
         return func.leaky_relu(conv(x), negative_slope=negative_slope)
     if conv.groups != 1 or conv.padding_mode != "zeros":
         raise NotImplementedError("conv_bias_leaky: groups == 1 and zero padding only")
-    return _ConvBiasLeaky.apply(x, conv.weight, conv.bias, tuple(conv.stride), tuple(_int_padding(conv)),
+    w = conv.weight if weight is None else weight
+    if x.dtype != torch.float32 or w.dtype != torch.float32:
+        raise TypeError("conv_bias_leaky: float32 only")
+    return _ConvBiasLeaky.apply(x, w, conv.bias, tuple(conv.stride), tuple(_int_padding(conv)),
                                 tuple(conv.dilation), negative_slope)
+
+
+def conv_plain(conv, x, weight=None):
+    """conv(x) with an optional replacement weight (padded / channels-last copy); bias and geometry from `conv`."""
+    w = conv.weight if weight is None else weight
+    return func.conv2d(x, w, conv.bias, conv.stride, _int_padding(conv) if x.is_cuda else conv.padding, conv.dilation)
+
+
+# ----------------------------------------------------------------------------- NHWC dense-block plumbing --------
+def round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+def pad_in_channels(weight, at, n_pad):
+    """Insert `n_pad` zero input channels at position `at` of a (Cout, Cin, kh, kw) weight and return it
+    channels-last: the counterpart of the zero channels `nhwc_concat` appends to the first concat of a dense block
+    (differentiable; the gradient of the inserted columns is dropped by the slicing)."""
+    if n_pad:
+        z = weight.new_zeros(weight.shape[0], n_pad, *weight.shape[2:])
+        weight = torch.cat([weight[:, :at], z, weight[:, at:]], dim=1)
+    return weight.contiguous(memory_format=CL)
+
+
+class _NhwcConcat(torch.autograd.Function):
+    """torch.cat(parts, dim=1) into a packed channels-last tensor with the channel count rounded up to `c_total`
+    (zero tail).  Parts may be NHWC or NCHW; each part's gradient comes back in the part's own layout."""
+
+    @staticmethod
+    def forward(ctx, c_total, *parts):
+        B, _, H, W = parts[0].shape
+        dev, dt = parts[0].device, parts[0].dtype
+        out = torch.empty((B, c_total, H, W), dtype=dt, device=dev, memory_format=CL)
+        meta, off = [], 0
+        with torch.cuda.device_of(out):
+            for p in parts:
+                if p.shape[0] != B or p.shape[2:] != (H, W) or p.dtype != torch.float32 or not p.is_cuda:
+                    raise ValueError("nhwc_concat: parts must be float32 CUDA tensors of equal batch and spatial size")
+                nhwc = is_nhwc(p)
+                if not nhwc:
+                    p = p.contiguous()
+                C = p.shape[1]
+                _lib.call("arf_nhwc_pack", out.data_ptr(), p.data_ptr(), B, H * W, C, c_total, off, int(nhwc),
+                          _lib.stream_ptr())
+                meta.append((C, off, nhwc))
+                off += C
+            if off > c_total:
+                raise ValueError("nhwc_concat: parts exceed c_total")
+            if off < c_total:
+                _lib.call("arf_nhwc_pack", out.data_ptr(), None, B, H * W, c_total - off, c_total, off, 1,
+                          _lib.stream_ptr())
+        ctx.meta = meta
+        ctx.dims = (B, H, W, c_total)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        B, H, W, c_total = ctx.dims
+        gout = gout.contiguous(memory_format=CL)
+        grads = [None]
+        with torch.cuda.device_of(gout):
+            for i, (C, off, nhwc) in enumerate(ctx.meta):
+                if not ctx.needs_input_grad[i + 1]:
+                    grads.append(None)
+                    continue
+                g = torch.empty((B, C, H, W), dtype=gout.dtype, device=gout.device,
+                                memory_format=CL if nhwc else torch.contiguous_format)
+                _lib.call("arf_nhwc_unpack", g.data_ptr(), gout.data_ptr(), B, H * W, C, c_total, off, int(nhwc),
+                          _lib.stream_ptr())
+                grads.append(g)
+        return tuple(grads)
+
+
+def nhwc_concat(parts, multiple=8):
+    """Channel concat of CUDA tensors into a packed channels-last tensor, channels padded up to `multiple`.
+    Returns (tensor, n_real_channels)."""
+    n = sum(p.shape[1] for p in parts)
+    return _NhwcConcat.apply(round_up(n, multiple), *parts), n

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as func
 
-from .fused_conv import conv_bias_leaky
+from .fused_conv import CL, conv_bias_leaky, conv_plain, nhwc_concat, pad_in_channels
 
 
 class _CudaOps:
@@ -88,12 +88,18 @@ class PWCFeaturePyramid(nn.Module):
                 c = out_c
             self._convs.append(group)
 
-    def forward(self, x, split_features_by_sample=False):
+    def forward(self, x, split_features_by_sample=False, nhwc=False):
+        """nhwc (CUDA only): activations and per-step weight copies are channels-last, so cuDNN's NHWC kernels run
+        without layout conversions; the returned features are channels-last tensors."""
         x = x * 2. - 1.
+        nhwc = nhwc and x.is_cuda
+        if nhwc:
+            x = x.contiguous(memory_format=CL)
         features = []
         for group in self._convs:
             for conv in group:
-                x = conv_bias_leaky(conv, x, self._leaky_relu_alpha)
+                x = conv_bias_leaky(conv, x, self._leaky_relu_alpha,
+                                    weight=conv.weight.contiguous(memory_format=CL) if nhwc else None)
             features.append(x)
         if split_features_by_sample:
             n = len(features[0])
@@ -104,10 +110,11 @@ class PWCFeaturePyramid(nn.Module):
 class PWCFlow(nn.Module):
     """uflow_model.py:96-362.  cfg needs `level_dropout` and `feature_norm`."""
 
-    def __init__(self, cfg, ops=None, stack_directions=True):
+    def __init__(self, cfg, ops=None, stack_directions=True, nhwc=True):
         super().__init__()
         self._ops = ops if ops is not None else _CudaOps()
         self._stack_directions = stack_directions
+        self._nhwc = nhwc      # CUDA only: channels-last conv stacks (see fused_conv.py); results are unchanged
         self._leaky_relu_alpha = 0.1
         self._drop_out_rate = cfg.level_dropout
         self._num_context_up_channels = 32
@@ -171,7 +178,74 @@ class PWCFlow(nn.Module):
         keep = (torch.rand(groups, device=like.device) > self._drop_out_rate).to(like.dtype)
         return keep.repeat_interleave(like.shape[0] // groups).view(-1, 1, 1, 1)
 
+    def _forward_2_frames_nhwc(self, feature_pyramid1, feature_pyramid2, groups=1):
+        """forward_2_frames with channels-last conv stacks.  Same operations in the same order; what changes is where
+        the bytes live: dense-block inputs are built by `nhwc_concat` as packed NHWC tensors with 8-aligned channel
+        counts (zero channels after the first concat of a level, zero weight columns to match), convolutions run on
+        cuDNN's NHWC kernels with no layout conversion, and only the tensors the NCHW hot-path kernels touch
+        (features for warp / cost volume, the 2-channel flow) are converted."""
+        ops = self._ops
+        alpha = self._leaky_relu_alpha
+        context = flow = flow_up = context_up = None
+        flows = []
+        for level in range(self._num_levels - 1, 0, -1):
+            features1, features2 = feature_pyramid1[level], feature_pyramid2[level]     # channels-last
+            f1 = features1.contiguous()
+            f2 = features2.contiguous()
+            warped2 = f2 if flow_up is None else ops.resample(f2, ops.flow_to_warp(flow_up))
+            f1n, w2n = normalize_features([f1, warped2], normalize=self._normalize_before_cost_volume,
+                                          center=self._normalize_before_cost_volume, moments_across_channels=True,
+                                          moments_across_images=True)
+            cost_volume = func.leaky_relu(ops.compute_cost_volume(f1n, w2n, max_displacement=4), negative_slope=alpha)
+            if flow_up is None:
+                parts = [cost_volume, features1]
+            elif context_up is None:
+                parts = [flow_up, cost_volume, features1]
+            else:
+                parts = [context_up, flow_up, cost_volume, features1]
+            x_in, c0 = nhwc_concat(parts)
+            n_pad = x_in.shape[1] - c0
+            dense = list(self._flow_layers[level])[:-1]
+            x_out = None
+            for i, layer in enumerate(dense):
+                conv = layer[0]
+                x_out = conv_bias_leaky(conv, x_in, alpha, weight=pad_in_channels(conv.weight, c0, n_pad))
+                if i + 1 < len(dense):
+                    x_in, _ = nhwc_concat([x_in, x_out])
+            context = x_out
+            last = self._flow_layers[level][-1]
+            flow = conv_plain(last, context, weight=last.weight.contiguous(memory_format=CL)).contiguous()
+
+            keep = self._keep(flow, groups)
+            if keep is not None:
+                context = context * keep
+                flow = flow * keep
+            if flow_up is not None and self._accumulate_flow:
+                flow = flow + flow_up
+            flow_up = ops.upsample(flow, is_flow=True)
+            up = self._context_up_layers[level]
+            context_up = func.conv_transpose2d(context, up.weight.contiguous(memory_format=CL), up.bias, up.stride,
+                                               up.padding, up.output_padding, up.groups, up.dilation)
+            flows.insert(0, flow)
+
+        refinement, c0 = nhwc_concat([context, flow])
+        n_pad = refinement.shape[1] - c0
+        refine = list(self._refine_model)          # conv, LeakyReLU, conv, LeakyReLU, ..., conv
+        for j, conv in enumerate(refine[:-1:2]):
+            w = pad_in_channels(conv.weight, c0, n_pad if j == 0 else 0)
+            refinement = conv_bias_leaky(conv, refinement, alpha, weight=w)
+        refinement = conv_plain(refine[-1], refinement, weight=refine[-1].weight.contiguous(memory_format=CL)).contiguous()
+        keep = self._keep(refinement, groups)
+        if keep is not None:
+            refinement = refinement * keep
+        flows[0] = flow + refinement
+        flows.insert(0, ops.upsample(flows[0], is_flow=True))
+        flows.insert(0, ops.upsample(flows[0], is_flow=True))
+        return flows
+
     def forward_2_frames(self, feature_pyramid1, feature_pyramid2, groups=1):
+        if self._nhwc and feature_pyramid1[-1].is_cuda:
+            return self._forward_2_frames_nhwc(feature_pyramid1, feature_pyramid2, groups)
         ops = self._ops
         context = flow = flow_up = context_up = None
         flows = []
@@ -233,14 +307,14 @@ class PWCFlow(nn.Module):
         res_dict = {}
         if with_bk and self._stack_directions:
             # one pyramid pass over [img1; img2], one decoder pass over [(1,2); (2,1)]
-            feats = self._feature_pyramid_extractor(torch.cat([x[:, 0:3], x[:, 3:6]], dim=0))
+            feats = self._feature_pyramid_extractor(torch.cat([x[:, 0:3], x[:, 3:6]], dim=0), nhwc=self._nhwc)
             p1 = feats
             p2 = [torch.cat([f[B:], f[:B]], dim=0) for f in feats]
             flows = self.forward_2_frames(p1, p2, groups=2)
             res_dict['flows_fw'] = [f[:B] for f in flows]
             res_dict['flows_bw'] = [f[B:] for f in flows]
             return res_dict
-        pyr = [self._feature_pyramid_extractor(x[:, 3 * i: 3 * i + 3]) for i in range(2)]
+        pyr = [self._feature_pyramid_extractor(x[:, 3 * i: 3 * i + 3], nhwc=self._nhwc) for i in range(2)]
         res_dict['flows_fw'] = self.forward_2_frames(pyr[0], pyr[1])
         if with_bk:
             res_dict['flows_bw'] = self.forward_2_frames(pyr[1], pyr[0])

@@ -172,6 +172,22 @@ int arf_bias_leaky_fwd(float* y, const float* bias, long long B, int C, long lon
 int arf_bias_leaky_bwd(const float* gy, const float* y, float* g, float* partials, float* dbias, long long B, int C,
                        long long HW, float slope, void* stream);
 
+/* Channels-last (NHWC) variants: y, gy, g are (rows = N*H*W) x C row-major; partials: arf_bias_leaky_nhwc_num_partials. */
+long long arf_bias_leaky_nhwc_num_partials(long long rows, int C);
+int arf_bias_leaky_nhwc_fwd(float* y, const float* bias, long long rows, int C, float slope, void* stream);
+int arf_bias_leaky_nhwc_bwd(const float* gy, const float* y, float* g, float* partials, float* dbias, long long rows,
+                            int C, float slope, void* stream);
+
+/* ---------------------------------------------------------------- NHWC concat ---------- */
+/* The decoder's torch.cat([...], dim=1) (models/uflow_model.py:189-205) into a packed NHWC tensor of Cd channels
+ * (Cd >= sum of the parts, the tail is padding): pack writes one part at channel offset c_off; src is NHWC
+ * (N,HW,Cs) when src_nhwc, else NCHW (N,Cs,HW); src == NULL writes zeros (padding channels).  unpack is the
+ * inverse (backward of the concat): part <- packed[..., c_off : c_off+Cs] in the part's own layout. */
+int arf_nhwc_pack(float* dst, const float* src, long long N, long long HW, int Cs, int Cd, int c_off, int src_nhwc,
+                  void* stream);
+int arf_nhwc_unpack(float* part, const float* packed, long long N, long long HW, int Cs, int Cd, int c_off,
+                    int part_nhwc, void* stream);
+
 /* ---------------------------------------------------------------- stencil-triangular ---- */
 /* matrix_vector_product_general / _T_general (utils/triag_solve.py:29-43, 59-73).
  * A: (N, 2*(k+1)^2, H, W), tap t = i*(k+1)+j occupies channels 2t, 2t+1 (u, v); X, Y: (N,2,H,W).

@@ -47,3 +47,72 @@ def test_conv_without_bias_and_without_input_grad():
     (rw,) = torch.autograd.grad(ref.sum(), [conv.weight])
     assert_close(out, ref, 1e-6)
     assert_close(gw, rw, 1e-4)     # TF32 convolutions (torch default) on both sides
+
+
+# --------------------------------------------------------------------------- channels-last plumbing
+@pytest.mark.parametrize("cin,cout,k,stride,padding,dilation,shape", [
+    (152, 128, 3, 1, "same", 1, (2, 152, 24, 32)),
+    (408, 96, 3, 1, "same", 1, (2, 408, 12, 16)),      # 96 output channels: 24 column groups (not a divisor of 256)
+    (40, 128, 3, 1, "same", 8, (1, 40, 33, 47)),
+    (3, 32, 3, 2, 1, 1, (2, 3, 40, 56)),
+    (32, 30, 3, 1, 1, 1, (2, 32, 9, 11)),              # C % 4 != 0 -> scalar epilogue
+])
+def test_conv_bias_leaky_channels_last(cin, cout, k, stride, padding, dilation, shape):
+    from arflow_b200.fused_conv import CL, conv_bias_leaky, is_nhwc
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(cin + cout)
+        conv = nn.Conv2d(cin, cout, k, stride=stride, padding=padding, dilation=dilation).cuda()
+        x = torch.randn(shape, device="cuda").contiguous(memory_format=CL).requires_grad_(True)
+        ref = func.leaky_relu(conv(x), negative_slope=0.1)
+        w = torch.randn_like(ref)
+        rg = torch.autograd.grad((ref * w).sum(), [x, conv.weight, conv.bias])
+        out = conv_bias_leaky(conv, x, 0.1, weight=conv.weight.contiguous(memory_format=CL))
+        og = torch.autograd.grad((out * w).sum(), [x, conv.weight, conv.bias])
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert is_nhwc(out)
+    assert_close(out, ref, 1e-5, "forward")
+    for a, b, name in zip(og, rg, ("grad x", "grad weight", "grad bias")):
+        assert_close(a, b, 2e-5, name)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 24, 32), (3, 7, 9)])
+def test_nhwc_concat_matches_torch_cat(B, H, W):
+    """Mixed NCHW / channels-last parts, unaligned offsets, zero tail; gradients return in each part's layout."""
+    from arflow_b200.fused_conv import CL, is_nhwc, nhwc_concat
+    gen = torch.Generator().manual_seed(B * H)
+    parts = [torch.randn(B, 32, H, W, generator=gen).cuda().contiguous(memory_format=CL),
+             torch.randn(B, 2, H, W, generator=gen).cuda(),
+             torch.randn(B, 81, H, W, generator=gen).cuda(),
+             torch.randn(B, 32, H, W, generator=gen).cuda().contiguous(memory_format=CL)]
+    parts = [p.requires_grad_(True) for p in parts]
+    out, n = nhwc_concat(parts)
+    assert n == 147 and out.shape == (B, 152, H, W) and is_nhwc(out)
+    ref = torch.cat([p.detach() for p in parts], dim=1)
+    assert torch.equal(out[:, :147], ref) and float(out[:, 147:].abs().max()) == 0.0
+    w = torch.randn(out.shape, generator=gen).cuda()
+    grads = torch.autograd.grad((out * w).sum(), parts)
+    off = 0
+    for p, g in zip(parts, grads):
+        assert torch.equal(g, w[:, off:off + p.shape[1]])
+        assert is_nhwc(g) == is_nhwc(p)
+        off += p.shape[1]
+    # aligned two-part concat of channels-last tensors (the dense-block step)
+    a = torch.randn(B, 152, H, W, generator=gen).cuda().contiguous(memory_format=CL)
+    b = torch.randn(B, 128, H, W, generator=gen).cuda().contiguous(memory_format=CL)
+    out2, n2 = nhwc_concat([a, b])
+    assert n2 == 280 and torch.equal(out2, torch.cat([a, b], dim=1))
+
+
+def test_pad_in_channels():
+    from arflow_b200.fused_conv import pad_in_channels
+    w = torch.randn(8, 147, 3, 3, device="cuda", requires_grad=True)
+    wp = pad_in_channels(w, 147, 5)
+    assert wp.shape == (8, 152, 3, 3) and float(wp[:, 147:].abs().max()) == 0.0 and torch.equal(wp[:, :147], w)
+    w2 = torch.randn(8, 275, 3, 3, device="cuda", requires_grad=True)
+    wp2 = pad_in_channels(w2, 147, 5)
+    assert torch.equal(wp2[:, :147], w2[:, :147]) and torch.equal(wp2[:, 152:], w2[:, 147:])
+    (g,) = torch.autograd.grad(wp2.sum(), [w2])
+    assert torch.equal(g, torch.ones_like(w2))

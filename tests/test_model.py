@@ -15,11 +15,11 @@ def _golden():
         return {k: z[k] for k in z.files}
 
 
-def _build(ops=None, device="cpu", stack=True):
+def _build(ops=None, device="cpu", stack=True, nhwc=True):
     from arflow_b200.uflow_model import PWCFlow
     cfg = types.SimpleNamespace(level_dropout=0.1, feature_norm=True)
     torch.manual_seed(123)
-    net = PWCFlow(cfg, ops=ops, stack_directions=stack)
+    net = PWCFlow(cfg, ops=ops, stack_directions=stack, nhwc=nhwc)
     net.init_weights()
     return net.to(device).eval()
 
@@ -47,12 +47,13 @@ def test_forward_matches_reference_on_cpu_ops(oracle, stack):
 
 
 @pytest.mark.gpu
-def test_forward_matches_reference_on_b200():
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_forward_matches_reference_on_b200(nhwc):
     g = _golden()
     old = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False      # compare against an fp32 CPU run of the reference
     try:
-        net = _build(device="cuda")
+        net = _build(device="cuda", nhwc=nhwc)
         with torch.no_grad():
             r = net(_input(g).cuda(), with_bk=True)
     finally:
@@ -86,3 +87,31 @@ def test_train_step_graph_matches_eager():
     assert_close(losses[1][:2, 0], losses[0][:2, 0], 1e-4, "first two losses, graph vs eager")
     assert_close(losses[1][:, 0], losses[0][:, 0], 1e-2, "loss trajectory graph vs eager")
     assert float(losses[0][2, 0]) != float(losses[0][0, 0])   # parameters are being updated
+
+
+@pytest.mark.gpu
+def test_channels_last_and_nchw_networks_agree_with_gradients():
+    """The channels-last decoder (packed NHWC dense blocks, padded weights) is the same function as the NCHW one:
+    outputs and parameter gradients agree (fp32 convolutions)."""
+    from arflow_b200.uflow_loss import UFlowLoss
+    lcfg = types.SimpleNamespace(edge_constant=150, w_smooth=4.0, w_census=1.0, with_bk=True, smooth_order=1)
+    x = torch.rand(2, 6, 192, 256, generator=torch.Generator().manual_seed(5)).cuda()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    res = []
+    try:
+        for nhwc in (False, True):
+            net = _build(device="cuda", nhwc=nhwc).train()
+            net._drop_out_rate = 0.0
+            r = net(x, with_bk=True)
+            flows = [torch.cat([a, b], 1) for a, b in zip(r['flows_fw'], r['flows_bw'])]
+            loss = UFlowLoss(lcfg)(flows, x)[0]
+            loss.backward()
+            res.append((flows[2].detach(), loss.detach(), {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}))
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert_close(res[1][0], res[0][0], 1e-4, "flows[2]")
+    assert_close(res[1][1], res[0][1], 1e-5, "loss")
+    assert res[0][2].keys() == res[1][2].keys()
+    for n in res[0][2]:
+        assert_close(res[1][2][n], res[0][2][n], 5e-3, "grad " + n)

@@ -15,8 +15,12 @@ prof () {  # name kernel-regex microbench-args...
 prof corr_fwd corr_fwd_md4 corr_fwd --shapes 64x32x96x128
 prof corr_bwd1 'corr_bwd_md4<\(bool\)0' corr_bwd --shapes 64x32x96x128
 prof corr_bwd2 'corr_bwd_md4<\(bool\)1' corr_bwd --shapes 64x32x96x128
-prof warp_fwd warp_fwd_kernel warp --shapes 64x32x96x128
-prof warp_bwd warp_bwd_kernel warp --shapes 64x32x96x128
+prof warp_fwd warp_fwd_kernel warp --flow smooth --shapes 64x32x96x128
+prof warp_gfield warp_gfield_win warp --flow smooth --shapes 64x32x96x128
+prof warp_gx warp_gx_csr warp --flow smooth --shapes 64x32x96x128
+prof warp_bwd_direct 'warp_bwd_kernel<8>' warp --flow smooth --shapes 16x32x96x128
 prof census_fwd census_fwd_kernel census --shapes 8x3x384x512
 prof census_bwd census_bwd_kernel census --shapes 8x3x384x512
-ls -la $OUT/*.ncu-rep
+prof stencil_fwd 'stencil_mv_kernel' stencil
+prof stencil_bwd 'stencil_mv_bwd_kernel' stencil
+ls -la $OUT/*_${TAG}.ncu-rep
