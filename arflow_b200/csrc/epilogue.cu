@@ -94,7 +94,7 @@ __global__ void bias_grad_finalize_kernel(const float* __restrict__ partials, fl
 inline int nchunks_of(long long HW) { return (int)((HW + kEChunk - 1) / kEChunk); }
 
 // ---- NHWC (channels-last) variants: y is a (rows = N*H*W) x C row-major matrix --------------------------------
-constexpr int kERows = 64;        // rows of the matrix handled by one CTA of the backward
+constexpr int kERows = 256;       // rows of the matrix handled by one CTA of the backward
 
 __global__ void __launch_bounds__(kEThreads)
 bias_leaky_nhwc_fwd_kernel(float* __restrict__ y, const float* __restrict__ bias, long long total, int C, float slope, int vec) {
@@ -178,13 +178,23 @@ bias_leaky_nhwc_bwd_kernel(const float* __restrict__ gy, const float* __restrict
     }
 }
 
-// dbias[c] = sum over CTAs of partials[cta*C + c]; thread <-> channel (coalesced rows), fixed order
-__global__ void bias_grad_nhwc_finalize_kernel(const float* __restrict__ partials, float* __restrict__ dbias, long long nblk, int C) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// dbias[c] = sum over CTAs of partials[cta*C + c].  block = (32 channels, 8 stripes over the CTAs): coalesced
+// 128-byte rows, 8-way parallel over the partial rows, fixed summation order.
+__global__ void __launch_bounds__(256)
+bias_grad_nhwc_finalize_kernel(const float* __restrict__ partials, float* __restrict__ dbias, long long nblk, int C) {
+    __shared__ double red[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
     double acc = 0.0;
-    for (long long i = 0; i < nblk; ++i) acc += (double)partials[i * C + c];
-    dbias[c] = (float)acc;
+    if (c < C)
+        for (long long i = threadIdx.y; i < nblk; i += 8) acc += (double)partials[i * C + c];
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+        dbias[c] = (float)s;
+    }
 }
 
 }  // namespace
@@ -218,7 +228,7 @@ extern "C" int arf_bias_leaky_nhwc_bwd(const float* gy, const float* y, float* g
         gy, y, g, dbias ? partials : nullptr, rows, C, slope, vec);
     ARF_CHECK_LAUNCH();
     if (dbias) {
-        bias_grad_nhwc_finalize_kernel<<<arf_cdiv(C, 128), 128, 0, st>>>(partials, dbias, nblk, C);
+        bias_grad_nhwc_finalize_kernel<<<arf_cdiv(C, 32), dim3(32, 8), 0, st>>>(partials, dbias, nblk, C);
         ARF_CHECK_LAUNCH();
     }
     return ARF_OK;

@@ -93,13 +93,21 @@ class PWCFeaturePyramid(nn.Module):
         without layout conversions; the returned features are channels-last tensors."""
         x = x * 2. - 1.
         nhwc = nhwc and x.is_cuda
+        n_pad = 0
         if nhwc:
-            x = x.contiguous(memory_format=CL)
+            # 3 image channels -> 8 (zeros): cuDNN's aligned NHWC kernels instead of its 3-channel fallback
+            c_img = x.shape[1]
+            x, _ = nhwc_concat([x])
+            n_pad = x.shape[1] - c_img
         features = []
+        first = True
         for group in self._convs:
             for conv in group:
-                x = conv_bias_leaky(conv, x, self._leaky_relu_alpha,
-                                    weight=conv.weight.contiguous(memory_format=CL) if nhwc else None)
+                w = None
+                if nhwc:
+                    w = pad_in_channels(conv.weight, conv.weight.shape[1], n_pad if first else 0)
+                x = conv_bias_leaky(conv, x, self._leaky_relu_alpha, weight=w)
+                first = False
             features.append(x)
         if split_features_by_sample:
             n = len(features[0])
