@@ -178,21 +178,21 @@ bias_leaky_nhwc_bwd_kernel(const float* __restrict__ gy, const float* __restrict
     }
 }
 
-// dbias[c] = sum over CTAs of partials[cta*C + c].  block = (32 channels, 8 stripes over the CTAs): coalesced
-// 128-byte rows, 8-way parallel over the partial rows, fixed summation order.
-__global__ void __launch_bounds__(256)
+// dbias[c] = sum over CTAs of partials[cta*C + c].  block = (32 channels, 32 stripes over the CTAs): coalesced
+// 128-byte rows, 32-way parallel over the partial rows, fixed summation order.
+__global__ void __launch_bounds__(1024)
 bias_grad_nhwc_finalize_kernel(const float* __restrict__ partials, float* __restrict__ dbias, long long nblk, int C) {
-    __shared__ double red[8][33];
+    __shared__ double red[32][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     double acc = 0.0;
     if (c < C)
-        for (long long i = threadIdx.y; i < nblk; i += 8) acc += (double)partials[i * C + c];
+        for (long long i = threadIdx.y; i < nblk; i += 32) acc += (double)partials[i * C + c];
     red[threadIdx.y][threadIdx.x] = acc;
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {
         double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+        for (int k = 0; k < 32; ++k) s += red[k][threadIdx.x];
         dbias[c] = (float)s;
     }
 }
@@ -228,7 +228,7 @@ extern "C" int arf_bias_leaky_nhwc_bwd(const float* gy, const float* y, float* g
         gy, y, g, dbias ? partials : nullptr, rows, C, slope, vec);
     ARF_CHECK_LAUNCH();
     if (dbias) {
-        bias_grad_nhwc_finalize_kernel<<<arf_cdiv(C, 32), dim3(32, 8), 0, st>>>(partials, dbias, nblk, C);
+        bias_grad_nhwc_finalize_kernel<<<arf_cdiv(C, 32), dim3(32, 32), 0, st>>>(partials, dbias, nblk, C);
         ARF_CHECK_LAUNCH();
     }
     return ARF_OK;

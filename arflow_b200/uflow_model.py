@@ -55,6 +55,45 @@ def compute_cost_volume(features1, features2, max_displacement):
     return _cv(features1, features2, max_displacement)
 
 
+# ----------------------------------------------------------------------------- channels-last decoder pieces ----
+# Shared by PWCFlow and PWCProbFlow (CUDA only).  Same operations in the same order as the reference's decoder; what
+# changes is where the bytes live: dense-block inputs are built by `nhwc_concat` as packed NHWC tensors with 8-aligned
+# channel counts (zero channels after the first concat of a level, zero weight columns to match), the convolutions
+# run on cuDNN's NHWC kernels without layout conversions, and only what the NCHW hot-path kernels touch (features
+# for warp / cost volume, the few output channels) is converted.
+def decoder_level_nhwc(layers, parts, alpha):
+    """One pyramid level's dense block + output convolution (models/uflow_model.py:189-205).
+    parts: tensors to concatenate (NCHW or channels-last).  Returns (context: channels-last, out: NCHW)."""
+    x_in, c0 = nhwc_concat(parts)
+    n_pad = x_in.shape[1] - c0
+    dense = list(layers)[:-1]
+    x_out = None
+    for i, layer in enumerate(dense):
+        conv = layer[0]                      # layer = Sequential(Conv2d, LeakyReLU)
+        x_out = conv_bias_leaky(conv, x_in, alpha, weight=pad_in_channels(conv.weight, c0, n_pad))
+        if i + 1 < len(dense):               # the reference also concatenates after the last layer; never read
+            x_in, _ = nhwc_concat([x_in, x_out])
+    last = layers[-1]
+    out = conv_plain(last, x_out, weight=last.weight.contiguous(memory_format=CL)).contiguous()
+    return x_out, out
+
+
+def refine_nhwc(refine_model, context, out, alpha):
+    """The dilated refinement stack on cat([context, out]) (models/uflow_model.py:212-216) -> NCHW."""
+    x, c0 = nhwc_concat([context, out])
+    n_pad = x.shape[1] - c0
+    refine = list(refine_model)              # conv, LeakyReLU, conv, LeakyReLU, ..., conv
+    for j, conv in enumerate(refine[:-1:2]):
+        x = conv_bias_leaky(conv, x, alpha, weight=pad_in_channels(conv.weight, c0, n_pad if j == 0 else 0))
+    return conv_plain(refine[-1], x, weight=refine[-1].weight.contiguous(memory_format=CL)).contiguous()
+
+
+def context_up_nhwc(up, context):
+    """ConvTranspose2d x2 of the context features, channels-last in and out."""
+    return func.conv_transpose2d(context, up.weight.contiguous(memory_format=CL), up.bias, up.stride, up.padding,
+                                 up.output_padding, up.groups, up.dilation)
+
+
 class PWCFeaturePyramid(nn.Module):
     """uflow_model.py:364-470 — five levels of three 3x3 convolutions, the first of each with stride 2."""
 
@@ -187,11 +226,7 @@ class PWCFlow(nn.Module):
         return keep.repeat_interleave(like.shape[0] // groups).view(-1, 1, 1, 1)
 
     def _forward_2_frames_nhwc(self, feature_pyramid1, feature_pyramid2, groups=1):
-        """forward_2_frames with channels-last conv stacks.  Same operations in the same order; what changes is where
-        the bytes live: dense-block inputs are built by `nhwc_concat` as packed NHWC tensors with 8-aligned channel
-        counts (zero channels after the first concat of a level, zero weight columns to match), convolutions run on
-        cuDNN's NHWC kernels with no layout conversion, and only the tensors the NCHW hot-path kernels touch
-        (features for warp / cost volume, the 2-channel flow) are converted."""
+        """forward_2_frames with channels-last conv stacks (see decoder_level_nhwc)."""
         ops = self._ops
         alpha = self._leaky_relu_alpha
         context = flow = flow_up = context_up = None
@@ -211,18 +246,7 @@ class PWCFlow(nn.Module):
                 parts = [flow_up, cost_volume, features1]
             else:
                 parts = [context_up, flow_up, cost_volume, features1]
-            x_in, c0 = nhwc_concat(parts)
-            n_pad = x_in.shape[1] - c0
-            dense = list(self._flow_layers[level])[:-1]
-            x_out = None
-            for i, layer in enumerate(dense):
-                conv = layer[0]
-                x_out = conv_bias_leaky(conv, x_in, alpha, weight=pad_in_channels(conv.weight, c0, n_pad))
-                if i + 1 < len(dense):
-                    x_in, _ = nhwc_concat([x_in, x_out])
-            context = x_out
-            last = self._flow_layers[level][-1]
-            flow = conv_plain(last, context, weight=last.weight.contiguous(memory_format=CL)).contiguous()
+            context, flow = decoder_level_nhwc(self._flow_layers[level], parts, alpha)
 
             keep = self._keep(flow, groups)
             if keep is not None:
@@ -231,18 +255,10 @@ class PWCFlow(nn.Module):
             if flow_up is not None and self._accumulate_flow:
                 flow = flow + flow_up
             flow_up = ops.upsample(flow, is_flow=True)
-            up = self._context_up_layers[level]
-            context_up = func.conv_transpose2d(context, up.weight.contiguous(memory_format=CL), up.bias, up.stride,
-                                               up.padding, up.output_padding, up.groups, up.dilation)
+            context_up = context_up_nhwc(self._context_up_layers[level], context)
             flows.insert(0, flow)
 
-        refinement, c0 = nhwc_concat([context, flow])
-        n_pad = refinement.shape[1] - c0
-        refine = list(self._refine_model)          # conv, LeakyReLU, conv, LeakyReLU, ..., conv
-        for j, conv in enumerate(refine[:-1:2]):
-            w = pad_in_channels(conv.weight, c0, n_pad if j == 0 else 0)
-            refinement = conv_bias_leaky(conv, refinement, alpha, weight=w)
-        refinement = conv_plain(refine[-1], refinement, weight=refine[-1].weight.contiguous(memory_format=CL)).contiguous()
+        refinement = refine_nhwc(self._refine_model, context, flow, alpha)
         keep = self._keep(refinement, groups)
         if keep is not None:
             refinement = refinement * keep

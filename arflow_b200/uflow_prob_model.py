@@ -17,20 +17,22 @@ import torch.nn as nn
 import torch.nn.functional as func
 
 from .fused_conv import conv_bias_leaky
-from .uflow_model import PWCFeaturePyramid, _CudaOps, normalize_features
+from .uflow_model import (PWCFeaturePyramid, _CudaOps, context_up_nhwc, decoder_level_nhwc, normalize_features,
+                          refine_nhwc)
 
 
 class PWCProbFlow(nn.Module):
     """uflow_prob_model.py:149-500.  cfg needs: out_channels, inv_cov, n_pyramids, mixture_weights,
     feature_norm, level_dropout."""
 
-    def __init__(self, cfg, ops=None, stack_directions=True):
+    def __init__(self, cfg, ops=None, stack_directions=True, nhwc=True):
         super().__init__()
         if getattr(cfg, "mixture_weights", False):
             raise NotImplementedError("PWCProbFlow: mixture_weights=True (MixtureWeightsNet) is not implemented")
         self.cfg = cfg
         self._ops = ops if ops is not None else _CudaOps()
         self._stack_directions = stack_directions
+        self._nhwc = nhwc      # CUDA only: channels-last conv stacks (fused_conv.py); results are unchanged
         self._leaky_relu_alpha = 0.1
         self._drop_out_rate = cfg.level_dropout
         self._num_context_up_channels = 32
@@ -131,24 +133,30 @@ class PWCProbFlow(nn.Module):
                                     features1.new_full((b, M, h, w), -(self._num_levels - 3) * self._diag_bias)], dim=1)
                 context_up = features1.new_zeros(b, self._num_context_up_channels, h, w)
 
+            nhwc = self._nhwc and features1.is_cuda
+            f1 = features1.contiguous() if nhwc else features1      # NCHW copies for the hot-path kernels
+            f2 = features2.contiguous() if nhwc else features2
             cost_volumes = []
             for k in range(L // 2):
-                warped2 = ops.resample(features2, ops.flow_to_warp(out_up[:, 2 * k:2 * k + 2]))
-                f1n, w2n = normalize_features([features1, warped2], normalize=self._normalize_before_cost_volume,
+                warped2 = ops.resample(f2, ops.flow_to_warp(out_up[:, 2 * k:2 * k + 2]))
+                f1n, w2n = normalize_features([f1, warped2], normalize=self._normalize_before_cost_volume,
                                               center=self._normalize_before_cost_volume, moments_across_channels=True,
                                               moments_across_images=True)
                 cost_volumes.append(func.leaky_relu(ops.compute_cost_volume(f1n, w2n, max_displacement=4),
                                                     negative_slope=self._leaky_relu_alpha))
-            x_in = torch.cat([context_up, out_up] + cost_volumes + [features1], dim=1)
-
-            dense = list(self._flow_layers[level])[:-1]
-            x_out = None
-            for i, layer in enumerate(dense):
-                x_out = conv_bias_leaky(layer[0], x_in, self._leaky_relu_alpha)
-                if i + 1 < len(dense):
-                    x_in = torch.cat([x_in, x_out], dim=1)
-            context = x_out
-            out = self._flow_layers[level][-1](context)
+            parts = [context_up, out_up] + cost_volumes + [features1]
+            if nhwc:
+                context, out = decoder_level_nhwc(self._flow_layers[level], parts, self._leaky_relu_alpha)
+            else:
+                x_in = torch.cat(parts, dim=1)
+                dense = list(self._flow_layers[level])[:-1]
+                x_out = None
+                for i, layer in enumerate(dense):
+                    x_out = conv_bias_leaky(layer[0], x_in, self._leaky_relu_alpha)
+                    if i + 1 < len(dense):
+                        x_in = torch.cat([x_in, x_out], dim=1)
+                context = x_out
+                out = self._flow_layers[level][-1](context)
 
             keep = self._keep(out, groups)
             if keep is not None:
@@ -159,16 +167,20 @@ class PWCProbFlow(nn.Module):
                                                              *out_up.shape[2:])], dim=1)
             out = out + out_up
             out_up = self.upsample_out(out)
-            context_up = self._context_up_layers[level](context)
+            up = self._context_up_layers[level]
+            context_up = context_up_nhwc(up, context) if nhwc else up(context)
             outs.insert(0, out)
 
         if out.shape[1] < L + M + N:
             out = torch.cat([out, out.new_zeros(out.shape[0], L + M + N - out.shape[1], *out.shape[2:])], dim=1)
-        refinement = torch.cat([context, out], dim=1)
-        refine = list(self._refine_model)          # conv, LeakyReLU, ..., conv
-        for conv in refine[:-1:2]:
-            refinement = conv_bias_leaky(conv, refinement, self._leaky_relu_alpha)
-        refinement = refine[-1](refinement)
+        if self._nhwc and out.is_cuda:
+            refinement = refine_nhwc(self._refine_model, context, out, self._leaky_relu_alpha)
+        else:
+            refinement = torch.cat([context, out], dim=1)
+            refine = list(self._refine_model)          # conv, LeakyReLU, ..., conv
+            for conv in refine[:-1:2]:
+                refinement = conv_bias_leaky(conv, refinement, self._leaky_relu_alpha)
+            refinement = refine[-1](refinement)
         keep = self._keep(refinement, groups)
         if keep is not None:
             refinement = refinement * keep
@@ -187,13 +199,13 @@ class PWCProbFlow(nn.Module):
         flows_fw, flows_bw = [], []
         for extractor in self._feature_pyramid_extractor:
             if with_bk and self._stack_directions:
-                feats = extractor(torch.cat([img1, img2], dim=0))
+                feats = extractor(torch.cat([img1, img2], dim=0), nhwc=self._nhwc)
                 swapped = [torch.cat([f[B:], f[:B]], dim=0) for f in feats]
                 outs = self.forward_2_frames(feats, swapped, groups=2)
                 flows_fw.append([o[:B] for o in outs])
                 flows_bw.append([o[B:] for o in outs])
             else:
-                feat1, feat2 = extractor(img1), extractor(img2)
+                feat1, feat2 = extractor(img1, nhwc=self._nhwc), extractor(img2, nhwc=self._nhwc)
                 flows_fw.append(self.forward_2_frames(feat1, feat2))
                 if with_bk:
                     flows_bw.append(self.forward_2_frames(feat2, feat1))

@@ -126,6 +126,16 @@ def alg_bytes(name, a):
         return B * Hh * Ww * 12
     if name == "arf_count_to_mask":
         return a[2] * 8
+    if name in ("arf_nhwc_pack", "arf_nhwc_unpack"):
+        return a[2] * a[3] * a[4] * 8                      # one part: read + write
+    if name == "arf_bias_leaky_fwd":
+        return a[2] * a[3] * a[4] * 8                      # in place: read + write
+    if name == "arf_bias_leaky_bwd":
+        return a[5] * a[6] * a[7] * 12                     # gy, y in; g out
+    if name == "arf_bias_leaky_nhwc_fwd":
+        return a[2] * a[3] * 8
+    if name == "arf_bias_leaky_nhwc_bwd":
+        return a[5] * a[6] * 12
     return 0
 
 
@@ -156,7 +166,15 @@ def alg_work(name, a):
     if name in ("arf_resize_bilinear_fwd", "arf_resize_bilinear_bwd"):
         n, Hi, Wi, Ho, Wo = a[2:7]
         return "N%d %dx%d->%dx%d" % (n, Hi, Wi, Ho, Wo), 0, 0
-    return "", 0, 0
+    if name in ("arf_nhwc_pack", "arf_nhwc_unpack"):
+        return "N%d HW%d C%d of %d %s" % (a[2], a[3], a[4], a[5], "nhwc" if a[7] else "nchw"), 0, 0
+    if name in ("arf_bias_leaky_nhwc_fwd", "arf_bias_leaky_nhwc_bwd"):
+        rows, C = (a[2], a[3]) if name.endswith("fwd") else (a[5], a[6])
+        return "rows%d C%d" % (rows, C), 0, 0
+    if name in ("arf_bias_leaky_fwd", "arf_bias_leaky_bwd"):
+        B, C, HW = a[2:5] if name.endswith("fwd") else a[5:8]
+        return "B%d C%d HW%d" % (B, C, HW), 0, 0
+    return "other", 0, 0
 
 
 # ----------------------------------------------------------------------------- reference arm --

@@ -22,10 +22,10 @@ def _golden(tag):
         return {k: z[k] for k in z.files}
 
 
-def _build(tag, seed, ops=None, device="cpu", stack=True):
+def _build(tag, seed, ops=None, device="cpu", stack=True, nhwc=True):
     from arflow_b200.uflow_prob_model import PWCProbFlow
     torch.manual_seed(seed)
-    net = PWCProbFlow(types.SimpleNamespace(**CFGS[tag]), ops=ops, stack_directions=stack)
+    net = PWCProbFlow(types.SimpleNamespace(**CFGS[tag]), ops=ops, stack_directions=stack, nhwc=nhwc)
     net.init_weights()
     return net.to(device).eval()
 
@@ -61,14 +61,15 @@ def test_mixture_weights_is_refused():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("nhwc", [False, True])
 @pytest.mark.parametrize("tag", ["nondiag", "diag2pyr"])
-def test_prob_model_matches_reference_on_b200(tag):
+def test_prob_model_matches_reference_on_b200(tag, nhwc):
     g = _golden(tag)
     seed = int(g["in0"])
     old = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False      # compare against an fp32 CPU run of the reference
     try:
-        net = _build(tag, seed, device="cuda")
+        net = _build(tag, seed, device="cuda", nhwc=nhwc)
         im1, im2 = _inputs(seed)
         with torch.no_grad():
             r = net(im1.cuda(), im2.cuda(), with_bk=True)
