@@ -39,6 +39,9 @@ PROTOTYPES = {
     "arf_smooth_num_partials": [c_int] * 3,
     "arf_smooth_fwd": [_P] * 4 + [c_int] * 8 + [c_float] * 3 + [_P],
     "arf_smooth_bwd": [_P] * 4 + [c_int] * 8 + [c_float] * 3 + [_P],
+    "arf_featnorm_workspace": [ctypes.c_longlong, ctypes.c_longlong],
+    "arf_featnorm_fwd": [_P] * 6 + [ctypes.c_longlong, ctypes.c_longlong, _P],
+    "arf_featnorm_bwd": [_P] * 9 + [ctypes.c_longlong, ctypes.c_longlong, _P],
     "arf_bias_leaky_num_partials": [ctypes.c_longlong, c_int, ctypes.c_longlong],
     "arf_bias_leaky_fwd": [_P, _P, ctypes.c_longlong, c_int, ctypes.c_longlong, c_float, _P],
     "arf_bias_leaky_bwd": [_P, _P, _P, _P, _P, ctypes.c_longlong, c_int, ctypes.c_longlong, c_float, _P],
@@ -57,7 +60,7 @@ PROTOTYPES = {
     "arf_resampler_bwd": [_P, _P, _P, ctypes.c_longlong, _P, _P, _P, _P, ctypes.c_longlong] + [c_int] * 4 + [ctypes.c_longlong, _P],
 }
 _RESTYPES = {"arf_error_string": ctypes.c_char_p, "arf_launch_count": ctypes.c_longlong,
-             "arf_bias_leaky_num_partials": ctypes.c_longlong, "arf_bias_leaky_nhwc_num_partials": ctypes.c_longlong}
+             "arf_featnorm_workspace": ctypes.c_longlong, "arf_bias_leaky_num_partials": ctypes.c_longlong, "arf_bias_leaky_nhwc_num_partials": ctypes.c_longlong}
 
 _lib = None
 

@@ -40,6 +40,13 @@ class UFlowTrainStep:
         self.use_graph = use_graph
         self.params = [p for p in model.parameters() if p.requires_grad]
         dev = self.params[0].device
+        if dev.type == "cuda" and getattr(model, "_nhwc", False):
+            # channels-last conv stacks (fused_conv.py): keep the 4-D weights channels-last in place, so the per-step
+            # `weight.contiguous(memory_format=channels_last)` of every layer is a no-op instead of a copy kernel
+            # (state_dict, shapes and values are unchanged; gradients and Adam state follow the parameter's strides)
+            for p in self.params:
+                if p.dim() == 4:
+                    p.data = p.data.contiguous(memory_format=torch.channels_last)
         # multi-GPU: flat gradient storage, parameter .grad tensors are views into it (16-byte aligned
         # spans so the accumulation kernels vectorise).  Single GPU: gradients are simply dropped to None
         # every step, autograd then hands its freshly written tensors over without an accumulate pass.
@@ -54,7 +61,8 @@ class UFlowTrainStep:
             total = off
             self.flat_grad = torch.zeros(total, device=dev, dtype=self.params[0].dtype)
             for p, (s0, e0) in zip(self.params, self._spans):
-                p.grad = self.flat_grad[s0:e0].view_as(p)
+                # same strides as the parameter (dense, possibly channels-last): the fused Adam walks raw memory
+                p.grad = self.flat_grad[s0:e0].as_strided(p.shape, p.stride())
         self.optimizer = torch.optim.Adam(self.params, lr=lr, betas=betas, eps=eps,
                                           capturable=dev.type == "cuda", fused=dev.type == "cuda")
         # buckets over the flat buffer; a bucket is all-reduced (on a side stream, overlapping the rest of

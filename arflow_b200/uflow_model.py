@@ -29,8 +29,51 @@ class _CudaOps:
         self.compute_cost_volume = correlation.compute_cost_volume
 
 
+class _FeatNormFunction(torch.autograd.Function):
+    """normalize_features for two maps with all four switches on (arf_featnorm_fwd / _bwd, csrc/normalize.cu)."""
+
+    @staticmethod
+    def forward(ctx, f1, f2):
+        from . import _lib
+        f1, f2 = f1.contiguous(), f2.contiguous()
+        B, n = f1.shape[0], f1[0].numel()
+        lib = _lib.load()
+        with torch.cuda.device_of(f1):
+            y1, y2 = torch.empty_like(f1), torch.empty_like(f2)
+            stats = torch.empty(B * 4, dtype=f1.dtype, device=f1.device)
+            ws = torch.empty(lib.arf_featnorm_workspace(B, n) // 8, dtype=torch.float64, device=f1.device)
+            _lib.call("arf_featnorm_fwd", _lib.dev_ptr(f1, "features1"), _lib.dev_ptr(f2, "features2"), _lib.dev_ptr(y1),
+                      _lib.dev_ptr(y2), _lib.dev_ptr(stats), ws.data_ptr(), B, n, _lib.stream_ptr())
+        ctx.save_for_backward(f1, f2, stats)
+        return y1, y2
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        from . import _lib
+        f1, f2, stats = ctx.saved_tensors
+        B, n = f1.shape[0], f1[0].numel()
+        g1 = torch.zeros_like(f1) if g1 is None else g1.contiguous()
+        g2 = torch.zeros_like(f2) if g2 is None else g2.contiguous()
+        lib = _lib.load()
+        with torch.cuda.device_of(f1):
+            d1 = torch.empty_like(f1) if ctx.needs_input_grad[0] else None
+            d2 = torch.empty_like(f2) if ctx.needs_input_grad[1] else None
+            coef = torch.empty(B * 2, dtype=f1.dtype, device=f1.device)
+            ws = torch.empty(lib.arf_featnorm_workspace(B, n) // 8, dtype=torch.float64, device=f1.device)
+            _lib.call("arf_featnorm_bwd", _lib.dev_ptr(f1), _lib.dev_ptr(f2), _lib.dev_ptr(g1, "grad"), _lib.dev_ptr(g2, "grad"),
+                      _lib.dev_ptr(stats), _lib.dev_ptr(d1, allow_none=True), _lib.dev_ptr(d2, allow_none=True),
+                      _lib.dev_ptr(coef), ws.data_ptr(), B, n, _lib.stream_ptr())
+        return d1, d2
+
+
 def normalize_features(feature_list, normalize, center, moments_across_channels, moments_across_images):
-    """uflow_model.py:8-50 — per-sample moments (unbiased variance), optionally shared by the images."""
+    """uflow_model.py:8-50 — per-sample moments (unbiased variance), optionally shared by the images.
+    The setting the networks use (two CUDA maps, all four switches on) runs as one fused reduction + one elementwise
+    pass each way; every other combination (and the CPU twin) is the reference's chain of torch ops."""
+    if (normalize and center and moments_across_channels and moments_across_images and len(feature_list) == 2
+            and feature_list[0].is_cuda and feature_list[0].dtype == torch.float32
+            and feature_list[0].shape == feature_list[1].shape):
+        return list(_FeatNormFunction.apply(feature_list[0], feature_list[1]))
     dim = [1, 2, 3] if moments_across_channels else [2, 3]
     stats = [torch.var_mean(f, dim=dim, keepdim=True) for f in feature_list]
     variances = [s[0] for s in stats]

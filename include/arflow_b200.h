@@ -161,6 +161,18 @@ int arf_smooth_bwd(const float* img, const float* flow, const float* gloss, floa
                    int order, int wstride, int woff, int penalty, float edge, float eps2, float final_scale,
                    void* stream);
 
+/* ---------------------------------------------------------------- feature normalisation */
+/* normalize_features([f1, f2], normalize=True, center=True, moments_across_channels=True, moments_across_images=True)
+ * (models/uflow_model.py:8-50; the only setting the models use, :163-170): per sample, mean and unbiased variance
+ * over all n = C*H*W elements of each map, averaged over the two maps; y_k = (f_k - mu) / sqrt(var + 1e-16).
+ * f*, y*, g*, d*: (B, n) dense; stats: B*4 floats (mu, std, mu_1, mu_2) written by fwd and read by bwd;
+ * coef: B*2 floats scratch; ws: arf_featnorm_workspace(B, n) bytes.  d1 / d2 may be NULL. */
+long long arf_featnorm_workspace(long long B, long long n);
+int arf_featnorm_fwd(const float* f1, const float* f2, float* y1, float* y2, float* stats, void* ws, long long B,
+                     long long n, void* stream);
+int arf_featnorm_bwd(const float* f1, const float* f2, const float* g1, const float* g2, const float* stats, float* d1,
+                     float* d2, float* coef, void* ws, long long B, long long n, void* stream);
+
 /* ---------------------------------------------------------------- conv epilogue -------- */
 /* Bias + leaky ReLU around the (cuDNN) convolutions of the PWC networks: nn.Conv2d(bias=True) followed by
  * nn.LeakyReLU / func.leaky_relu (models/uflow_model.py:134-135, 427-436; uflow_prob_model.py:445-456).

@@ -116,3 +116,34 @@ def test_pad_in_channels():
     assert torch.equal(wp2[:, :147], w2[:, :147]) and torch.equal(wp2[:, 152:], w2[:, 147:])
     (g,) = torch.autograd.grad(wp2.sum(), [w2])
     assert torch.equal(g, torch.ones_like(w2))
+
+
+# --------------------------------------------------------------------------- normalize_features (row N1)
+@pytest.mark.parametrize("shape", [(2, 32, 24, 32), (3, 32, 6, 8), (1, 5, 7, 9)])
+def test_normalize_features_fused_matches_torch_chain(shape):
+    """arf_featnorm_* against the reference's chain of torch ops (models/uflow_model.py:8-50), values and gradients."""
+    from arflow_b200.uflow_model import normalize_features
+    gen = torch.Generator().manual_seed(shape[1] + shape[2])
+    f1 = (torch.randn(shape, generator=gen) * 0.7 + 0.3).cuda().requires_grad_(True)
+    f2 = (torch.randn(shape, generator=gen) * 1.3 - 0.2).cuda().requires_grad_(True)
+
+    def chain(a, b):      # the reference's own formulation, in float64 for the ground truth
+        a, b = a.double(), b.double()
+        stats = [torch.var_mean(t, dim=[1, 2, 3], keepdim=True) for t in (a, b)]
+        mean = (stats[0][1] + stats[1][1]) / 2
+        std = torch.sqrt((stats[0][0] + stats[1][0]) / 2 + 1e-16)
+        return (a - mean) / std, (b - mean) / std
+    r1, r2 = chain(f1, f2)
+    w1, w2 = torch.randn(shape, generator=gen).cuda(), torch.randn(shape, generator=gen).cuda()
+    rg = torch.autograd.grad((r1 * w1).sum() + (r2 * w2).sum(), [f1, f2])
+    y1, y2 = normalize_features([f1, f2], normalize=True, center=True, moments_across_channels=True,
+                                moments_across_images=True)
+    og = torch.autograd.grad((y1 * w1).sum() + (y2 * w2).sum(), [f1, f2])
+    assert_close(y1, r1, 1e-5, "y1")
+    assert_close(y2, r2, 1e-5, "y2")
+    assert_close(og[0], rg[0], 1e-4, "grad f1")
+    assert_close(og[1], rg[1], 1e-4, "grad f2")
+    # only one output used downstream
+    (g_only,) = torch.autograd.grad((normalize_features([f1, f2], True, True, True, True)[0] * w1).sum(), [f2])
+    (r_only,) = torch.autograd.grad((chain(f1, f2)[0] * w1).sum(), [f2])
+    assert_close(g_only, r_only, 1e-4, "grad f2 through y1 only")
