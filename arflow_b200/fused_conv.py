@@ -85,10 +85,10 @@ class _ConvBiasLeaky(torch.autograd.Function):
         return gx, gw, db, None, None, None, None
 
 
-def conv_bias_leaky(conv, x, negative_slope, weight=None):
-    """leaky_relu(conv(x)) for an nn.Conv2d `conv` (groups 1); `weight` overrides conv.weight (padded / channels-last
-    copy).  CUDA tensors take the fused path; a CPU tensor means the caller is the oracle-backed CPU twin of the
-    network (tests, bench.py's cpu_baseline) and gets plain torch."""
+def conv_bias_leaky(conv, x, negative_slope, weight=None, bias=None):
+    """leaky_relu(conv(x)) for an nn.Conv2d `conv` (groups 1); `weight` / `bias` override conv.weight / conv.bias
+    (padded / channels-last copies).  CUDA tensors take the fused path; a CPU tensor means the caller is the
+    oracle-backed CPU twin of the network (tests, bench.py's cpu_baseline) and gets plain torch."""
     if not x.is_cuda:
         return func.leaky_relu(conv(x), negative_slope=negative_slope)
     if conv.groups != 1 or conv.padding_mode != "zeros":
@@ -96,8 +96,8 @@ def conv_bias_leaky(conv, x, negative_slope, weight=None):
     w = conv.weight if weight is None else weight
     if x.dtype != torch.float32 or w.dtype != torch.float32:
         raise TypeError("conv_bias_leaky: float32 only")
-    return _ConvBiasLeaky.apply(x, w, conv.bias, tuple(conv.stride), tuple(_int_padding(conv)),
-                                tuple(conv.dilation), negative_slope)
+    return _ConvBiasLeaky.apply(x, w, conv.bias if bias is None else bias, tuple(conv.stride),
+                                tuple(_int_padding(conv)), tuple(conv.dilation), negative_slope)
 
 
 def conv_plain(conv, x, weight=None):
@@ -111,14 +111,36 @@ def round_up(n, m):
     return (n + m - 1) // m * m
 
 
-def pad_in_channels(weight, at, n_pad):
-    """Insert `n_pad` zero input channels at position `at` of a (Cout, Cin, kh, kw) weight and return it
-    channels-last: the counterpart of the zero channels `nhwc_concat` appends to the first concat of a dense block
-    (differentiable; the gradient of the inserted columns is dropped by the slicing)."""
-    if n_pad:
-        z = weight.new_zeros(weight.shape[0], n_pad, *weight.shape[2:])
-        weight = torch.cat([weight[:, :at], z, weight[:, at:]], dim=1)
+def pad_weight(weight, in_pads=(), out_pad=0):
+    """Channels-last copy of a (Cout, Cin, kh, kw) weight with zero input channels inserted and zero output channels
+    appended.  in_pads: [(position in the ORIGINAL input-channel order, count), ...] in increasing position — the
+    counterpart of the zero channels the NHWC dense block carries (the tail of its first concat, the tail of a
+    convolution output that was widened to a multiple of 64).  Differentiable; the gradients of the inserted rows and
+    columns are dropped by the slicing."""
+    pieces, prev = [], 0
+    for at, n in in_pads:
+        if n:
+            pieces.append(weight[:, prev:at])
+            pieces.append(weight.new_zeros(weight.shape[0], n, *weight.shape[2:]))
+            prev = at
+    if pieces:
+        pieces.append(weight[:, prev:])
+        weight = torch.cat(pieces, dim=1)
+    if out_pad:
+        weight = torch.cat([weight, weight.new_zeros(out_pad, *weight.shape[1:])], dim=0)
     return weight.contiguous(memory_format=CL)
+
+
+def pad_in_channels(weight, at, n_pad):
+    """pad_weight with one insertion."""
+    return pad_weight(weight, [(at, n_pad)])
+
+
+def out_channel_pad(cout):
+    """Zero output channels to append so that cuDNN runs its sm_100 forward kernel: measured on B200 / cuDNN 9
+    (tools/conv_layer_probe.py, 16 x 408 x 96 x 128 NHWC, 3x3): Cout = 96 -> 1107 us forward (sm80 fallback kernel),
+    Cout = 128 -> 281 us, 64 -> 205 us, 32 -> 152 us; the backward costs 656 vs 587 us."""
+    return (-cout) % 64 if cout > 64 else 0
 
 
 class _NhwcConcat(torch.autograd.Function):

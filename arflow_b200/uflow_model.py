@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as func
 
-from .fused_conv import CL, conv_bias_leaky, conv_plain, nhwc_concat, pad_in_channels
+from .fused_conv import CL, conv_bias_leaky, conv_plain, nhwc_concat, out_channel_pad, pad_in_channels, pad_weight
 
 
 class _CudaOps:
@@ -104,18 +104,31 @@ def compute_cost_volume(features1, features2, max_displacement):
 # channel counts (zero channels after the first concat of a level, zero weight columns to match), the convolutions
 # run on cuDNN's NHWC kernels without layout conversions, and only what the NCHW hot-path kernels touch (features
 # for warp / cost volume, the few output channels) is converted.
+def _conv_leaky_padded(conv, x, alpha, in_pads):
+    """conv + bias + leaky on a channels-last input that carries zero channels at `in_pads`; the output is widened
+    with zero channels to a width cuDNN has a fast kernel for (out_channel_pad).  Returns (y, n_zero_out_channels)."""
+    op = out_channel_pad(conv.out_channels)
+    bias = conv.bias
+    if op and bias is not None:
+        bias = torch.cat([bias, bias.new_zeros(op)])
+    return conv_bias_leaky(conv, x, alpha, weight=pad_weight(conv.weight, in_pads, op), bias=bias), op
+
+
 def decoder_level_nhwc(layers, parts, alpha):
     """One pyramid level's dense block + output convolution (models/uflow_model.py:189-205).
     parts: tensors to concatenate (NCHW or channels-last).  Returns (context: channels-last, out: NCHW)."""
-    x_in, c0 = nhwc_concat(parts)
-    n_pad = x_in.shape[1] - c0
+    x_in, real = nhwc_concat(parts)
+    pads = [(real, x_in.shape[1] - real)]      # (position in the real channel order, zero channels carried there)
     dense = list(layers)[:-1]
     x_out = None
     for i, layer in enumerate(dense):
         conv = layer[0]                      # layer = Sequential(Conv2d, LeakyReLU)
-        x_out = conv_bias_leaky(conv, x_in, alpha, weight=pad_in_channels(conv.weight, c0, n_pad))
+        x_out, op = _conv_leaky_padded(conv, x_in, alpha, pads)
         if i + 1 < len(dense):               # the reference also concatenates after the last layer; never read
             x_in, _ = nhwc_concat([x_in, x_out])
+            real += conv.out_channels
+            if op:
+                pads.append((real, op))
     last = layers[-1]
     out = conv_plain(last, x_out, weight=last.weight.contiguous(memory_format=CL)).contiguous()
     return x_out, out
@@ -124,11 +137,12 @@ def decoder_level_nhwc(layers, parts, alpha):
 def refine_nhwc(refine_model, context, out, alpha):
     """The dilated refinement stack on cat([context, out]) (models/uflow_model.py:212-216) -> NCHW."""
     x, c0 = nhwc_concat([context, out])
-    n_pad = x.shape[1] - c0
+    pads = [(c0, x.shape[1] - c0)]
     refine = list(refine_model)              # conv, LeakyReLU, conv, LeakyReLU, ..., conv
-    for j, conv in enumerate(refine[:-1:2]):
-        x = conv_bias_leaky(conv, x, alpha, weight=pad_in_channels(conv.weight, c0, n_pad if j == 0 else 0))
-    return conv_plain(refine[-1], x, weight=refine[-1].weight.contiguous(memory_format=CL)).contiguous()
+    for conv in refine[:-1:2]:
+        x, op = _conv_leaky_padded(conv, x, alpha, pads)
+        pads = [(conv.out_channels, op)]
+    return conv_plain(refine[-1], x, weight=pad_weight(refine[-1].weight, pads)).contiguous()
 
 
 def context_up_nhwc(up, context):
