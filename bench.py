@@ -357,8 +357,12 @@ def main_b200(args):
             # dominant = the (entry point, problem shape) with the most device time per step
             (name, label), k = max(per_shape.items(), key=lambda kv: kv[1]["ms"])
             ach = k["bytes"] / (k["ms"] * 1e-3) / 1e9
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get("%s [%s]" % (name, label), {}).get("dram_bytes")
             roof = {"kernel": "%s [%s]" % (name, label), "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                    "frac": ach / hbm, "traffic": None, "peak_source": how,
+                    "frac": ach / hbm, "traffic": traffic, "peak_source": how,
                     "avg_launch_us": 1e3 * k["ms"] / k["calls"], "bytes_per_launch": k["bytes"] / k["calls"],
                     "step_share": k["ms"] / n_prof / (ms_total / args.steps),
                     "fp32_tflops": k["flops"] / (k["ms"] * 1e-3) / 1e12,

@@ -194,6 +194,59 @@ def main():
                 return lambda: lib.arf_trisolve(A.data_ptr(), Bc.data_ptr(), Cc.data_ptr(), Dc.data_ptr(), X.data_ptr(),
                                                 Y.data_ptr(), N * 2, H, W, 0, cs())
             report("trisolve", (N, 2, H, W), N * 2 * H * W * 24, N * 2 * H * W * 8, *time_graph(mkt, N * 2 * H * W * 24))
+    if args.what in ("glue", "all"):
+        # the streaming kernels around the cuDNN convolutions (fused_conv.py): L1-level shapes of the chairs_uflow step
+        nrows, C = 16 * 96 * 128, 128
+
+        def mk_epi(kind):
+            def make():
+                y = torch.randn(nrows, C, device="cuda")
+                gy = torch.randn(nrows, C, device="cuda")
+                g = torch.empty_like(y)
+                b = torch.randn(C, device="cuda")
+                db = torch.empty(C, device="cuda")
+                part = torch.empty(lib.arf_bias_leaky_nhwc_num_partials(nrows, C), device="cuda")
+                if kind == "fwd":
+                    return lambda: lib.arf_bias_leaky_nhwc_fwd(y.data_ptr(), b.data_ptr(), nrows, C, 0.1, cs())
+                return lambda: lib.arf_bias_leaky_nhwc_bwd(gy.data_ptr(), y.data_ptr(), g.data_ptr(), part.data_ptr(),
+                                                           db.data_ptr(), nrows, C, 0.1, cs())
+            return make
+        report("epilogue_fwd", (nrows, C), nrows * C * 8, nrows * C * 2, *time_graph(mk_epi("fwd"), nrows * C * 8))
+        report("epilogue_bwd", (nrows, C), nrows * C * 12, nrows * C * 2, *time_graph(mk_epi("bwd"), nrows * C * 12))
+        for (Cs, Cd, nhwc) in [(408, 504, 1), (81, 152, 0), (32, 152, 1)]:
+            N, HW = 16, 96 * 128
+
+            def mk_pack(kind):
+                def make():
+                    src = torch.randn(N * HW * Cs, device="cuda")
+                    dst = torch.empty(N * HW * Cd, device="cuda")
+                    if kind == "pack":
+                        return lambda: lib.arf_nhwc_pack(dst.data_ptr(), src.data_ptr(), N, HW, Cs, Cd, 0 if nhwc else 34, nhwc, cs())
+                    return lambda: lib.arf_nhwc_unpack(src.data_ptr(), dst.data_ptr(), N, HW, Cs, Cd, 0 if nhwc else 34, nhwc, cs())
+                return make
+            tag = "nhwc" if nhwc else "nchw"
+            report("pack_" + tag, (N, Cs, Cd, HW), N * HW * Cs * 8, 0, *time_graph(mk_pack("pack"), N * HW * Cs * 8))
+            report("unpack_" + tag, (N, Cs, Cd, HW), N * HW * Cs * 8, 0, *time_graph(mk_pack("unpack"), N * HW * Cs * 8))
+        n = 32 * 96 * 128
+
+        def mk_norm(kind):
+            def make():
+                B = 16
+                f1, f2 = torch.randn(B, n, device="cuda"), torch.randn(B, n, device="cuda")
+                g1, g2 = torch.randn(B, n, device="cuda"), torch.randn(B, n, device="cuda")
+                y1, y2 = torch.empty_like(f1), torch.empty_like(f2)
+                stats, coef = torch.empty(B * 4, device="cuda"), torch.empty(B * 2, device="cuda")
+                ws = torch.empty(lib.arf_featnorm_workspace(B, n) // 8, dtype=torch.float64, device="cuda")
+                lib.arf_featnorm_fwd(f1.data_ptr(), f2.data_ptr(), y1.data_ptr(), y2.data_ptr(), stats.data_ptr(), ws.data_ptr(), B, n, cs())
+                if kind == "fwd":
+                    return lambda: lib.arf_featnorm_fwd(f1.data_ptr(), f2.data_ptr(), y1.data_ptr(), y2.data_ptr(), stats.data_ptr(),
+                                                        ws.data_ptr(), B, n, cs())
+                return lambda: lib.arf_featnorm_bwd(f1.data_ptr(), f2.data_ptr(), g1.data_ptr(), g2.data_ptr(), stats.data_ptr(),
+                                                    y1.data_ptr(), y2.data_ptr(), coef.data_ptr(), ws.data_ptr(), B, n, cs())
+            return make
+        # fwd: read both maps twice (moments, apply) + write both; bwd: read f, g twice + write both
+        report("featnorm_fwd", (16, 32, 96, 128), 16 * n * 4 * 6, 16 * n * 8, *time_graph(mk_norm("fwd"), 16 * n * 24))
+        report("featnorm_bwd", (16, 32, 96, 128), 16 * n * 4 * 10, 16 * n * 12, *time_graph(mk_norm("bwd"), 16 * n * 40))
     if args.csv:
         os.makedirs(os.path.dirname(args.csv), exist_ok=True)
         with open(args.csv, "w") as f:
