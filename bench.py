@@ -183,6 +183,13 @@ def run_cpu_reference(steps, warmup, batch):
     GPU box).  Each step = one full train step on `batch` synthetic pairs of 384x512."""
     import torch
     import oracle.arflow_oracle as orc
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its children)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    if torch.get_num_threads() < avail:
+        torch.set_num_threads(avail)
     cores = torch.get_num_threads()
     step = orc.CpuTrainStep(seed=0)
     gen = torch.Generator().manual_seed(0)
