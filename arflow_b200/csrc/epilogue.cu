@@ -121,7 +121,7 @@ bias_leaky_nhwc_fwd_kernel(float* __restrict__ y, const float* __restrict__ bias
 // rows t / G, t / G + 256 / G, ...; the per-thread column sums are reduced through shared memory, one partial row
 // of C sums per CTA.
 __global__ void __launch_bounds__(kEThreads)
-bias_leaky_nhwc_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y, float* __restrict__ g,
+bias_leaky_nhwc_bwd_kernel(const float* __restrict__ gy, long long gy_ld, const float* __restrict__ y, float* __restrict__ g,
                            float* __restrict__ partials, long long rows, int C, float slope, int vec) {
     extern __shared__ float sacc[];          // kEThreads * 4 floats
     const long long r0 = (long long)blockIdx.x * kERows;
@@ -135,8 +135,9 @@ bias_leaky_nhwc_bwd_kernel(const float* __restrict__ gy, const float* __restrict
         const int cg = threadIdx.x % G, rstep = kEThreads / G;      // threads >= rstep * G stay idle (G = 24: 240 of 256)
         for (long long r = r0 + threadIdx.x / G; r < r1 && threadIdx.x < rstep * G; r += rstep) {
             const long long e = r * C + (long long)cg * w;
+            const long long eg = r * gy_ld + (long long)cg * w;     // gy may be a column slice of a wider matrix
             if (vec) {
-                const float4 a = *reinterpret_cast<const float4*>(gy + e);
+                const float4 a = *reinterpret_cast<const float4*>(gy + eg);
                 const float4 b = *reinterpret_cast<const float4*>(y + e);
                 float4 o;
                 o.x = b.x > 0.f ? a.x : a.x * slope; o.y = b.y > 0.f ? a.y : a.y * slope;
@@ -144,7 +145,7 @@ bias_leaky_nhwc_bwd_kernel(const float* __restrict__ gy, const float* __restrict
                 *reinterpret_cast<float4*>(g + e) = o;
                 acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
             } else {
-                const float a = gy[e];
+                const float a = gy[eg];
                 const float o = y[e] > 0.f ? a : a * slope;
                 g[e] = o;
                 acc.x += o;
@@ -164,7 +165,8 @@ bias_leaky_nhwc_bwd_kernel(const float* __restrict__ gy, const float* __restrict
     } else {
         // generic widths (not used by the PWC networks): elementwise pass, then each thread sums whole columns
         for (long long e = r0 * C + threadIdx.x; e < r1 * C; e += kEThreads) {
-            const float a = gy[e];
+            const long long r = e / C;
+            const float a = gy[r * gy_ld + (e - r * C)];
             g[e] = y[e] > 0.f ? a : a * slope;
         }
         if (partials) {
@@ -217,15 +219,21 @@ extern "C" int arf_bias_leaky_nhwc_fwd(float* y, const float* bias, long long ro
 
 extern "C" int arf_bias_leaky_nhwc_bwd(const float* gy, const float* y, float* g, float* partials, float* dbias,
                                        long long rows, int C, float slope, void* stream) {
+    return arf_bias_leaky_nhwc_bwd_ld(gy, C, y, g, partials, dbias, rows, C, slope, stream);
+}
+
+extern "C" int arf_bias_leaky_nhwc_bwd_ld(const float* gy, long long gy_ld, const float* y, float* g, float* partials,
+                                          float* dbias, long long rows, int C, float slope, void* stream) {
     ARF_REQUIRE(gy && y && g);
-    ARF_REQUIRE(rows > 0 && C > 0);
+    ARF_REQUIRE(rows > 0 && C > 0 && gy_ld >= C);
     if (dbias) ARF_REQUIRE(partials != nullptr);
     const long long nblk = (rows + kERows - 1) / kERows;
     if (nblk > 0x7fffffffLL) return ARF_EINVAL;
-    const int vec = ((uintptr_t)gy % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)g % 16 == 0) && (C % 4 == 0);
+    const int vec = ((uintptr_t)gy % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)g % 16 == 0) && (C % 4 == 0) &&
+                    (gy_ld % 4 == 0);
     cudaStream_t st = (cudaStream_t)stream;
     bias_leaky_nhwc_bwd_kernel<<<(unsigned)nblk, kEThreads, kEThreads * 4 * sizeof(float), st>>>(
-        gy, y, g, dbias ? partials : nullptr, rows, C, slope, vec);
+        gy, gy_ld, y, g, dbias ? partials : nullptr, rows, C, slope, vec);
     ARF_CHECK_LAUNCH();
     if (dbias) {
         bias_grad_nhwc_finalize_kernel<<<arf_cdiv(C, 32), dim3(32, 32), 0, st>>>(partials, dbias, nblk, C);

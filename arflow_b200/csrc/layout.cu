@@ -16,7 +16,7 @@ namespace {
 constexpr int kLThreads = 256;
 
 // NHWC part <-> NHWC destination slice: rows = N*HW pixels, part width Cs, destination width Cd, offset c_off.
-template <bool kPack>
+template <bool kPack, bool kAcc = false>
 __global__ void __launch_bounds__(kLThreads)
 nhwc_part_kernel(float* __restrict__ dst, const float* __restrict__ src, long long rows, int Cs, int Cd, int c_off, int vec) {
     // kPack:  dst[row*Cd + c_off + c] = src[row*Cs + c]     (src may be null: zero fill)
@@ -31,7 +31,12 @@ nhwc_part_kernel(float* __restrict__ dst, const float* __restrict__ src, long lo
                 float4 v = src ? *reinterpret_cast<const float4*>(src + row * Cs + c) : make_float4(0.f, 0.f, 0.f, 0.f);
                 *reinterpret_cast<float4*>(dst + row * Cd + c_off + c) = v;
             } else {
-                *reinterpret_cast<float4*>(dst + row * Cs + c) = *reinterpret_cast<const float4*>(src + row * Cd + c_off + c);
+                float4 v = *reinterpret_cast<const float4*>(src + row * Cd + c_off + c);
+                if (kAcc) {     // unpack-accumulate: part += packed slice (gradient of a tensor that is also a conv input)
+                    const float4 o = *reinterpret_cast<const float4*>(dst + row * Cs + c);
+                    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                }
+                *reinterpret_cast<float4*>(dst + row * Cs + c) = v;
             }
         }
     } else {
@@ -40,7 +45,7 @@ nhwc_part_kernel(float* __restrict__ dst, const float* __restrict__ src, long lo
             const long long row = e / Cs;
             const int c = (int)(e - row * Cs);
             if (kPack) dst[row * Cd + c_off + c] = src ? src[row * Cs + c] : 0.f;
-            else dst[row * Cs + c] = src[row * Cd + c_off + c];
+            else dst[row * Cs + c] = (kAcc ? dst[row * Cs + c] : 0.f) + src[row * Cd + c_off + c];
         }
     }
 }
@@ -161,6 +166,19 @@ extern "C" int arf_nhwc_unpack(float* part, const float* packed, long long N, lo
     ARF_REQUIRE(part && packed);
     int rc = launch_part<false>(part, packed, N, HW, Cs, Cd, c_off, part_nhwc, (cudaStream_t)stream);
     if (rc) return rc;
+    ARF_CHECK_LAUNCH();
+    return ARF_OK;
+}
+
+// part (NHWC, width Cs) += packed[..., c_off : c_off + Cs]
+extern "C" int arf_nhwc_unpack_add(float* part, const float* packed, long long N, long long HW, int Cs, int Cd, int c_off,
+                                   void* stream) {
+    ARF_REQUIRE(part && packed);
+    if (N <= 0 || HW <= 0 || Cs <= 0 || Cd <= 0 || c_off < 0 || c_off + Cs > Cd) return ARF_EINVAL;
+    const int vec = (Cs % 4 == 0) && (Cd % 4 == 0) && (c_off % 4 == 0) && ((uintptr_t)packed % 16 == 0) && ((uintptr_t)part % 16 == 0);
+    const long long work = N * HW * (vec ? Cs / 4 : Cs);
+    nhwc_part_kernel<false, true><<<arf_grid_1d(work, kLThreads, 16), kLThreads, 0, (cudaStream_t)stream>>>(
+        part, packed, N * HW, Cs, Cd, c_off, vec);
     ARF_CHECK_LAUNCH();
     return ARF_OK;
 }

@@ -197,3 +197,90 @@ def nhwc_concat(parts, multiple=8):
     Returns (tensor, n_real_channels)."""
     n = sum(p.shape[1] for p in parts)
     return _NhwcConcat.apply(round_up(n, multiple), *parts), n
+
+
+class _DenseBlockNhwc(torch.autograd.Function):
+    """The PWC decoder's dense block (models/uflow_model.py:195-198) on packed channels-last tensors, with a manual
+    backward:   x_{i+1} = cat([x_i, leaky(conv_i(x_i) + b_i)]),   returns the last layer's output.
+
+    Forward = what conv_bias_leaky + nhwc_concat do layer by layer.  The backward walks the layers in reverse and
+    keeps ONE running gradient G (w.r.t. x_{i+1}): a layer's output gradient is read straight out of G's column
+    slice by the fused epilogue backward (no unpack copy), and the part of G that belongs to x_i is accumulated
+    into the convolution's input gradient in place (arf_nhwc_unpack_add) — instead of autograd's unpack copy of
+    both parts plus a separate add per layer.  All weights arrive padded / channels-last (pad_weight)."""
+
+    @staticmethod
+    def forward(ctx, slope, geom, x0, *wb):
+        n = len(wb) // 2
+        ws, bs = wb[:n], wb[n:]
+        xs, ys = [x0], []
+        x = x0
+        B, _, H, W = x0.shape
+        rows = B * H * W
+        for i in range(n):
+            stride, padding, dilation = geom[i]
+            y = func.conv2d(x, ws[i], None, stride, padding, dilation).contiguous(memory_format=CL)
+            C = y.shape[1]
+            with torch.cuda.device_of(y):
+                _lib.call("arf_bias_leaky_nhwc_fwd", y.data_ptr(),
+                          bs[i].contiguous().data_ptr() if bs[i] is not None else None, rows, C, float(slope),
+                          _lib.stream_ptr())
+                ys.append(y)
+                if i + 1 < n:
+                    cin = x.shape[1]
+                    nx = torch.empty((B, cin + C, H, W), dtype=x.dtype, device=x.device, memory_format=CL)
+                    _lib.call("arf_nhwc_pack", nx.data_ptr(), x.data_ptr(), B, H * W, cin, cin + C, 0, 1, _lib.stream_ptr())
+                    _lib.call("arf_nhwc_pack", nx.data_ptr(), y.data_ptr(), B, H * W, C, cin + C, cin, 1, _lib.stream_ptr())
+                    x = nx
+                    xs.append(x)
+        ctx.save_for_backward(*xs, *ys, *ws)
+        ctx.cfg = (n, float(slope), geom, [b is not None for b in bs])
+        return ys[-1]
+
+    @staticmethod
+    def backward(ctx, gy_last):
+        n, slope, geom, has_bias = ctx.cfg
+        saved = ctx.saved_tensors
+        xs, ys, ws = saved[:n], saved[n:2 * n], saved[2 * n:3 * n]
+        lib = _lib.load()
+        B, _, H, W = xs[0].shape
+        rows = B * H * W
+        gws, gbs = [None] * n, [None] * n
+        G = None            # gradient w.r.t. xs[i + 1] (packed, width = xs[i + 1].shape[1])
+        with torch.cuda.device_of(xs[0]):
+            for i in range(n - 1, -1, -1):
+                y = ys[i]
+                C, cin = y.shape[1], xs[i].shape[1]
+                if G is None:
+                    gy = gy_last.contiguous(memory_format=CL)
+                    gy_ptr, gy_ld = gy.data_ptr(), C
+                else:
+                    gy_ptr, gy_ld = G.data_ptr() + 4 * cin, G.shape[1]      # columns [cin, cin + C) of G
+                need_b = has_bias[i] and ctx.needs_input_grad[3 + n + i]
+                g = torch.empty_like(y)
+                db = torch.empty(C, dtype=y.dtype, device=y.device) if need_b else None
+                part = (torch.empty(lib.arf_bias_leaky_nhwc_num_partials(rows, C), dtype=y.dtype, device=y.device)
+                        if need_b else None)
+                _lib.call("arf_bias_leaky_nhwc_bwd_ld", gy_ptr, gy_ld, y.data_ptr(), g.data_ptr(),
+                          part.data_ptr() if need_b else None, db.data_ptr() if need_b else None, rows, C, slope,
+                          _lib.stream_ptr())
+                stride, padding, dilation = geom[i]
+                need_x = i > 0 or ctx.needs_input_grad[2]
+                gx, gw, _ = torch.ops.aten.convolution_backward(
+                    g, xs[i], ws[i], None, list(stride), list(padding), list(dilation), False, [0, 0], 1,
+                    [bool(need_x), bool(ctx.needs_input_grad[3 + i]), False])
+                if need_x:
+                    gx = gx.contiguous(memory_format=CL)
+                    if G is not None:
+                        _lib.call("arf_nhwc_unpack_add", gx.data_ptr(), G.data_ptr(), B, H * W, cin, G.shape[1], 0,
+                                  _lib.stream_ptr())
+                G = gx
+                gws[i], gbs[i] = gw, db
+        return (None, None, G, *gws, *gbs)
+
+
+def dense_block_nhwc(x0, convs, weights, biases, negative_slope):
+    """x0: packed channels-last input; convs: the nn.Conv2d modules (geometry); weights / biases: their padded,
+    channels-last weights and (padded) biases.  Returns the last layer's activated output (channels-last)."""
+    geom = tuple((tuple(c.stride), tuple(_int_padding(c)), tuple(c.dilation)) for c in convs)
+    return _DenseBlockNhwc.apply(negative_slope, geom, x0, *weights, *biases)

@@ -15,7 +15,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as func
 
-from .fused_conv import CL, conv_bias_leaky, conv_plain, nhwc_concat, out_channel_pad, pad_in_channels, pad_weight
+from .fused_conv import (CL, conv_bias_leaky, conv_plain, dense_block_nhwc, nhwc_concat, out_channel_pad,
+                         pad_in_channels, pad_weight)
 
 
 class _CudaOps:
@@ -119,19 +120,21 @@ def decoder_level_nhwc(layers, parts, alpha):
     parts: tensors to concatenate (NCHW or channels-last).  Returns (context: channels-last, out: NCHW)."""
     x_in, real = nhwc_concat(parts)
     pads = [(real, x_in.shape[1] - real)]      # (position in the real channel order, zero channels carried there)
-    dense = list(layers)[:-1]
-    x_out = None
-    for i, layer in enumerate(dense):
-        conv = layer[0]                      # layer = Sequential(Conv2d, LeakyReLU)
-        x_out, op = _conv_leaky_padded(conv, x_in, alpha, pads)
-        if i + 1 < len(dense):               # the reference also concatenates after the last layer; never read
-            x_in, _ = nhwc_concat([x_in, x_out])
-            real += conv.out_channels
-            if op:
-                pads.append((real, op))
+    convs = [layer[0] for layer in list(layers)[:-1]]      # layer = Sequential(Conv2d, LeakyReLU)
+    weights, biases = [], []
+    for i, conv in enumerate(convs):
+        # the last layer's output is not concatenated again: keep its width (the reference's final cat is never read)
+        op = out_channel_pad(conv.out_channels) if i + 1 < len(convs) else 0
+        weights.append(pad_weight(conv.weight, pads, op))
+        b = conv.bias
+        biases.append(torch.cat([b, b.new_zeros(op)]) if (op and b is not None) else b)
+        real += conv.out_channels
+        if op:
+            pads = pads + [(real, op)]
+    context = dense_block_nhwc(x_in, convs, weights, biases, alpha)
     last = layers[-1]
-    out = conv_plain(last, x_out, weight=last.weight.contiguous(memory_format=CL)).contiguous()
-    return x_out, out
+    out = conv_plain(last, context, weight=last.weight.contiguous(memory_format=CL)).contiguous()
+    return context, out
 
 
 def refine_nhwc(refine_model, context, out, alpha):

@@ -189,6 +189,10 @@ long long arf_bias_leaky_nhwc_num_partials(long long rows, int C);
 int arf_bias_leaky_nhwc_fwd(float* y, const float* bias, long long rows, int C, float slope, void* stream);
 int arf_bias_leaky_nhwc_bwd(const float* gy, const float* y, float* g, float* partials, float* dbias, long long rows,
                             int C, float slope, void* stream);
+/* same, with gy a column slice of a wider row-major matrix: row stride gy_ld >= C (the dense block's backward reads
+ * a layer's output gradient straight out of the gradient of the concatenation it went into) */
+int arf_bias_leaky_nhwc_bwd_ld(const float* gy, long long gy_ld, const float* y, float* g, float* partials, float* dbias,
+                               long long rows, int C, float slope, void* stream);
 
 /* ---------------------------------------------------------------- NHWC concat ---------- */
 /* The decoder's torch.cat([...], dim=1) (models/uflow_model.py:189-205) into a packed NHWC tensor of Cd channels
@@ -199,6 +203,10 @@ int arf_nhwc_pack(float* dst, const float* src, long long N, long long HW, int C
                   void* stream);
 int arf_nhwc_unpack(float* part, const float* packed, long long N, long long HW, int Cs, int Cd, int c_off,
                     int part_nhwc, void* stream);
+/* part (NHWC) += packed[..., c_off : c_off+Cs]: the gradient of a tensor that feeds both a convolution and the next
+ * concatenation is accumulated in place instead of unpack + add */
+int arf_nhwc_unpack_add(float* part, const float* packed, long long N, long long HW, int Cs, int Cd, int c_off,
+                        void* stream);
 
 /* ---------------------------------------------------------------- stencil-triangular ---- */
 /* matrix_vector_product_general / _T_general (utils/triag_solve.py:29-43, 59-73).

@@ -147,3 +147,36 @@ def test_normalize_features_fused_matches_torch_chain(shape):
     (g_only,) = torch.autograd.grad((normalize_features([f1, f2], True, True, True, True)[0] * w1).sum(), [f2])
     (r_only,) = torch.autograd.grad((chain(f1, f2)[0] * w1).sum(), [f2])
     assert_close(g_only, r_only, 1e-4, "grad f2 through y1 only")
+
+
+def test_dense_block_manual_backward_matches_layerwise_autograd():
+    """_DenseBlockNhwc (one running gradient, strided epilogue backward, accumulate-unpack) against the same block
+    composed from conv_bias_leaky + nhwc_concat under plain autograd."""
+    from arflow_b200.fused_conv import CL, conv_bias_leaky, dense_block_nhwc, nhwc_concat, pad_weight
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(3)
+        widths, c0 = [128, 128, 96, 64, 32], 152
+        convs, cin = [], c0
+        for c in widths:
+            convs.append(nn.Conv2d(cin, c, 3, padding="same").cuda())
+            cin += c
+        x0 = torch.randn(2, c0, 12, 16, device="cuda").contiguous(memory_format=CL).requires_grad_(True)
+        params = [p for conv in convs for p in (conv.weight, conv.bias)]
+
+        x = x0
+        for i, conv in enumerate(convs):
+            y = conv_bias_leaky(conv, x, 0.1, weight=pad_weight(conv.weight))
+            if i + 1 < len(convs):
+                x, _ = nhwc_concat([x, y])
+        w = torch.randn_like(y)
+        ref = torch.autograd.grad((y * w).sum(), [x0] + params)
+
+        out = dense_block_nhwc(x0, convs, [pad_weight(c.weight) for c in convs], [c.bias for c in convs], 0.1)
+        got = torch.autograd.grad((out * w).sum(), [x0] + params)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert torch.equal(out, y)
+    for a, b in zip(got, ref):
+        assert_close(a, b, 2e-5)
