@@ -152,6 +152,71 @@ int launch_part(float* dst, const float* src, long long N, long long HW, int Cs,
 
 }  // namespace
 
+// Weight re-layout for the channels-last conv stacks: dst (Co_d, Ci_d, KH, KW) in channels-last memory order
+// [co][kh][kw][ci] <- src (Co_s, Ci_s, KH, KW) with arbitrary strides, zero input channels inserted at up to four
+// positions and zero output channels appended (to_padded = 1); or the inverse gather (to_padded = 0: the weight
+// gradient back in the parameter's own layout, inserted rows / columns dropped).  One launch per layer and
+// direction instead of zeros + cat + contiguous (+ their autograd counterparts).
+struct PadMap {
+    int n;           // number of insertions
+    int at[4];       // position in the ORIGINAL input-channel order (increasing)
+    int cnt[4];      // zero channels inserted there
+};
+
+__global__ void __launch_bounds__(256)
+pad_weight_kernel(float* __restrict__ dst, const float* __restrict__ src, int Co_s, int Ci_s, int KH, int KW, int Co_d,
+                  int Ci_d, long long s_co, long long s_ci, long long s_kh, long long s_kw, PadMap pm, int to_padded) {
+    // iterate over the PADDED index space; (co, kh, kw, cip) with cip fastest (the padded tensor's memory order)
+    const long long total = (long long)Co_d * KH * KW * Ci_d;
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const int cip = (int)(e % Ci_d);
+        long long t = e / Ci_d;
+        const int kw = (int)(t % KW); t /= KW;
+        const int kh = (int)(t % KH);
+        const int co = (int)(t / KH);
+        // padded input channel -> original input channel (or -1 inside an inserted block)
+        int ci = cip, shift = 0;
+        bool zero = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < pm.n) {
+                const int start = pm.at[k] + shift;          // first padded index of the inserted block
+                if (cip >= start + pm.cnt[k]) { shift += pm.cnt[k]; }
+                else if (cip >= start) { zero = true; }
+            }
+        }
+        ci = cip - shift;
+        zero = zero || co >= Co_s || ci >= Ci_s;
+        const long long so = (long long)co * s_co + (long long)ci * s_ci + (long long)kh * s_kh + (long long)kw * s_kw;
+        if (to_padded) dst[e] = zero ? 0.f : __ldg(src + so);
+        else if (!zero) dst[so] = __ldg(src + e);             // dst = original layout, src = padded
+    }
+}
+
+extern "C" int arf_pad_weight(float* dst, const float* src, int Co, int Ci, int KH, int KW, int Co_pad, int Ci_pad,
+                              long long s_co, long long s_ci, long long s_kh, long long s_kw, int n_pads,
+                              const int* pad_at, const int* pad_cnt, int to_padded, void* stream) {
+    ARF_REQUIRE(dst && src);
+    ARF_REQUIRE(Co > 0 && Ci > 0 && KH > 0 && KW > 0 && Co_pad >= Co && Ci_pad >= Ci && n_pads >= 0 && n_pads <= 4);
+    PadMap pm;
+    pm.n = n_pads;
+    int extra = 0;
+    for (int k = 0; k < 4; ++k) {
+        pm.at[k] = k < n_pads ? pad_at[k] : 0;
+        pm.cnt[k] = k < n_pads ? pad_cnt[k] : 0;
+        if (k < n_pads) {
+            if (pad_at[k] < 0 || pad_at[k] > Ci || pad_cnt[k] < 0 || (k > 0 && pad_at[k] < pad_at[k - 1])) return ARF_EINVAL;
+            extra += pad_cnt[k];
+        }
+    }
+    if (Ci + extra != Ci_pad) return ARF_EINVAL;
+    const long long total = (long long)Co_pad * KH * KW * Ci_pad;
+    pad_weight_kernel<<<arf_grid_1d(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(dst, src, Co, Ci, KH, KW, Co_pad, Ci_pad, s_co,
+                                                                                   s_ci, s_kh, s_kw, pm, to_padded);
+    ARF_CHECK_LAUNCH();
+    return ARF_OK;
+}
+
 extern "C" int arf_nhwc_pack(float* dst, const float* src, long long N, long long HW, int Cs, int Cd, int c_off,
                              int src_nhwc, void* stream) {
     ARF_REQUIRE(dst);

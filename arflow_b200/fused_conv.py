@@ -111,24 +111,68 @@ def round_up(n, m):
     return (n + m - 1) // m * m
 
 
+_ZEROS = {}
+
+
+def _zeros_cl(like, shape):
+    """A cached all-zero channels-last block (read-only by convention): the padding pieces of pad_weight are the same
+    every step, so they are allocated and filled once instead of costing a fill kernel per layer and step."""
+    key = (tuple(shape), like.device, like.dtype)
+    z = _ZEROS.get(key)
+    if z is None:
+        z = torch.zeros(shape, dtype=like.dtype, device=like.device)
+        if len(shape) == 4:
+            z = z.contiguous(memory_format=CL)
+        _ZEROS[key] = z
+    return z
+
+
+class _PadWeight(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weight, in_pads, out_pad):
+        import ctypes
+        Co, Ci, KH, KW = weight.shape
+        pads = [(int(a), int(n)) for a, n in in_pads if n]
+        if len(pads) > 4:
+            raise ValueError("pad_weight: at most four insertions")
+        Cip, Cop = Ci + sum(n for _, n in pads), Co + int(out_pad)
+        at = (ctypes.c_int * 4)(*([a for a, _ in pads] + [0] * (4 - len(pads))))
+        cnt = (ctypes.c_int * 4)(*([n for _, n in pads] + [0] * (4 - len(pads))))
+        with torch.cuda.device_of(weight):
+            out = torch.empty((Cop, Cip, KH, KW), dtype=weight.dtype, device=weight.device, memory_format=CL)
+            _lib.call("arf_pad_weight", out.data_ptr(), weight.data_ptr(), Co, Ci, KH, KW, Cop, Cip, *weight.stride(),
+                      len(pads), at, cnt, 1, _lib.stream_ptr())
+        ctx.meta = (weight.shape, weight.stride(), pads, Cop, Cip)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        import ctypes
+        shape, stride, pads, Cop, Cip = ctx.meta
+        Co, Ci, KH, KW = shape
+        gout = gout.contiguous(memory_format=CL)
+        at = (ctypes.c_int * 4)(*([a for a, _ in pads] + [0] * (4 - len(pads))))
+        cnt = (ctypes.c_int * 4)(*([n for _, n in pads] + [0] * (4 - len(pads))))
+        with torch.cuda.device_of(gout):
+            gw = torch.empty_strided(shape, stride, dtype=gout.dtype, device=gout.device)   # the parameter's own layout
+            _lib.call("arf_pad_weight", gw.data_ptr(), gout.data_ptr(), Co, Ci, KH, KW, Cop, Cip, *stride,
+                      len(pads), at, cnt, 0, _lib.stream_ptr())
+        return gw, None, None
+
+
 def pad_weight(weight, in_pads=(), out_pad=0):
     """Channels-last copy of a (Cout, Cin, kh, kw) weight with zero input channels inserted and zero output channels
     appended.  in_pads: [(position in the ORIGINAL input-channel order, count), ...] in increasing position — the
     counterpart of the zero channels the NHWC dense block carries (the tail of its first concat, the tail of a
-    convolution output that was widened to a multiple of 64).  Differentiable; the gradients of the inserted rows and
-    columns are dropped by the slicing."""
-    pieces, prev = [], 0
-    for at, n in in_pads:
-        if n:
-            pieces.append(weight[:, prev:at])
-            pieces.append(weight.new_zeros(weight.shape[0], n, *weight.shape[2:]))
-            prev = at
-    if pieces:
-        pieces.append(weight[:, prev:])
-        weight = torch.cat(pieces, dim=1)
-    if out_pad:
-        weight = torch.cat([weight, weight.new_zeros(out_pad, *weight.shape[1:])], dim=0)
-    return weight.contiguous(memory_format=CL)
+    convolution output that was widened to a multiple of 64).  One kernel each way (arf_pad_weight); the gradient comes
+    back in the parameter's own layout with the inserted rows and columns dropped."""
+    pads = [(a, n) for a, n in in_pads if n]
+    if not pads and not out_pad and weight.is_contiguous(memory_format=CL):
+        return weight                      # channels-last parameter (train_step.py), nothing to insert: no copy
+    if not weight.is_cuda:
+        raise RuntimeError("pad_weight: CUDA tensors only (the CPU twin of the networks does not pad)")
+    dense = weight.is_contiguous() or weight.is_contiguous(memory_format=CL)
+    return _PadWeight.apply(weight if dense else weight.contiguous(), tuple(pads), int(out_pad))
 
 
 def pad_in_channels(weight, at, n_pad):

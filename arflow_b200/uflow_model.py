@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as func
 
-from .fused_conv import (CL, conv_bias_leaky, conv_plain, dense_block_nhwc, nhwc_concat, out_channel_pad,
+from .fused_conv import (CL, _zeros_cl, conv_bias_leaky, conv_plain, dense_block_nhwc, nhwc_concat, out_channel_pad,
                          pad_in_channels, pad_weight)
 
 
@@ -111,7 +111,7 @@ def _conv_leaky_padded(conv, x, alpha, in_pads):
     op = out_channel_pad(conv.out_channels)
     bias = conv.bias
     if op and bias is not None:
-        bias = torch.cat([bias, bias.new_zeros(op)])
+        bias = torch.cat([bias, _zeros_cl(bias, (op,))])
     return conv_bias_leaky(conv, x, alpha, weight=pad_weight(conv.weight, in_pads, op), bias=bias), op
 
 
@@ -127,7 +127,7 @@ def decoder_level_nhwc(layers, parts, alpha):
         op = out_channel_pad(conv.out_channels) if i + 1 < len(convs) else 0
         weights.append(pad_weight(conv.weight, pads, op))
         b = conv.bias
-        biases.append(torch.cat([b, b.new_zeros(op)]) if (op and b is not None) else b)
+        biases.append(torch.cat([b, _zeros_cl(b, (op,))]) if (op and b is not None) else b)
         real += conv.out_channels
         if op:
             pads = pads + [(real, op)]

@@ -201,6 +201,12 @@ int arf_bias_leaky_nhwc_bwd_ld(const float* gy, long long gy_ld, const float* y,
  * inverse (backward of the concat): part <- packed[..., c_off : c_off+Cs] in the part's own layout. */
 int arf_nhwc_pack(float* dst, const float* src, long long N, long long HW, int Cs, int Cd, int c_off, int src_nhwc,
                   void* stream);
+/* Convolution weight (Co,Ci,KH,KW; element strides s_*) <-> its channels-last copy (Co_pad,Ci_pad,KH,KW) with
+ * pad_cnt[k] zero input channels inserted at original position pad_at[k] (k < n_pads <= 4, increasing) and zero output
+ * channels appended.  to_padded = 1: dst = padded copy; 0: dst = gradient in the parameter's layout, src = padded. */
+int arf_pad_weight(float* dst, const float* src, int Co, int Ci, int KH, int KW, int Co_pad, int Ci_pad, long long s_co,
+                   long long s_ci, long long s_kh, long long s_kw, int n_pads, const int* pad_at, const int* pad_cnt,
+                   int to_padded, void* stream);
 int arf_nhwc_unpack(float* part, const float* packed, long long N, long long HW, int Cs, int Cd, int c_off,
                     int part_nhwc, void* stream);
 /* part (NHWC) += packed[..., c_off : c_off+Cs]: the gradient of a tensor that feeds both a convolution and the next
