@@ -328,3 +328,32 @@ def dense_block_nhwc(x0, convs, weights, biases, negative_slope):
     channels-last weights and (padded) biases.  Returns the last layer's activated output (channels-last)."""
     geom = tuple((tuple(c.stride), tuple(_int_padding(c)), tuple(c.dilation)) for c in convs)
     return _DenseBlockNhwc.apply(negative_slope, geom, x0, *weights, *biases)
+
+
+class _ToNchw(torch.autograd.Function):
+    """channels-last -> NCHW copy (and NCHW -> channels-last for the gradient) through the tiled transpose of
+    arf_nhwc_unpack / arf_nhwc_pack: the features the NCHW hot-path kernels (warp, cost volume) read."""
+
+    @staticmethod
+    def forward(ctx, x):
+        B, C, H, W = x.shape
+        with torch.cuda.device_of(x):
+            out = torch.empty((B, C, H, W), dtype=x.dtype, device=x.device)
+            _lib.call("arf_nhwc_unpack", out.data_ptr(), x.data_ptr(), B, H * W, C, C, 0, 0, _lib.stream_ptr())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        B, C, H, W = g.shape
+        with torch.cuda.device_of(g):
+            out = torch.empty((B, C, H, W), dtype=g.dtype, device=g.device, memory_format=CL)
+            _lib.call("arf_nhwc_pack", out.data_ptr(), g.data_ptr(), B, H * W, C, C, 0, 0, _lib.stream_ptr())
+        return out
+
+
+def to_nchw(x):
+    """x.contiguous() for a channels-last CUDA float32 tensor, with a coalesced transpose both ways."""
+    if not (x.is_cuda and x.dtype == torch.float32 and is_nhwc(x)):
+        return x.contiguous()
+    return _ToNchw.apply(x)

@@ -16,7 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as func
 
 from .fused_conv import (CL, _zeros_cl, conv_bias_leaky, conv_plain, dense_block_nhwc, nhwc_concat, out_channel_pad,
-                         pad_in_channels, pad_weight)
+                         pad_in_channels, pad_weight, to_nchw)
 
 
 class _CudaOps:
@@ -293,8 +293,8 @@ class PWCFlow(nn.Module):
         flows = []
         for level in range(self._num_levels - 1, 0, -1):
             features1, features2 = feature_pyramid1[level], feature_pyramid2[level]     # channels-last
-            f1 = features1.contiguous()
-            f2 = features2.contiguous()
+            f1 = to_nchw(features1)
+            f2 = to_nchw(features2)
             warped2 = f2 if flow_up is None else ops.resample(f2, ops.flow_to_warp(flow_up))
             f1n, w2n = normalize_features([f1, warped2], normalize=self._normalize_before_cost_volume,
                                           center=self._normalize_before_cost_volume, moments_across_channels=True,

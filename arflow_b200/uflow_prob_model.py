@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as func
 
-from .fused_conv import conv_bias_leaky
+from .fused_conv import conv_bias_leaky, to_nchw
 from .uflow_model import (PWCFeaturePyramid, _CudaOps, context_up_nhwc, decoder_level_nhwc, normalize_features,
                           refine_nhwc)
 
@@ -134,8 +134,8 @@ class PWCProbFlow(nn.Module):
                 context_up = features1.new_zeros(b, self._num_context_up_channels, h, w)
 
             nhwc = self._nhwc and features1.is_cuda
-            f1 = features1.contiguous() if nhwc else features1      # NCHW copies for the hot-path kernels
-            f2 = features2.contiguous() if nhwc else features2
+            f1 = to_nchw(features1) if nhwc else features1      # NCHW copies for the hot-path kernels
+            f2 = to_nchw(features2) if nhwc else features2
             cost_volumes = []
             for k in range(L // 2):
                 warped2 = ops.resample(f2, ops.flow_to_warp(out_up[:, 2 * k:2 * k + 2]))
