@@ -15,6 +15,13 @@
 // tile is staged in shared memory with 16-byte cp.async (flow gradient), and the scatter pattern of the tile is
 // sorted once into a CSR table so the source gradient needs one coalesced red.global.add per touched element
 // and channel instead of four scattered ones per pixel and channel.
+//
+// Tuning record (B200, tools/microbench.py warp): the forward gains nothing from shared-memory staging (74 vs 76 us at
+// 64x32x96x128) and runs direct; fp32 shared-memory atomics are CAS loops (~1 lane-add/clk/SM), which is why the
+// source gradient sorts its scatter into a CSR table instead; aggregating a lane's east taps into its neighbour's
+// west taps by shuffle ("warp-aggregated atomics") halves the red.global.add count for smooth flows but was SLOWER
+// in the direct kernel (16x32x96x128 smooth: 93 vs 87 us) - the extra registers cost more occupancy than the
+// atomics saved; 32-bit tap offsets with advancing plane pointers: slower (84 vs 74 us forward).
 #include "common.cuh"
 
 int g_warp_variant = 0;   // test hook (arf_debug_set key 3): 1 = force the direct kernels, 2 = force the window kernels

@@ -393,7 +393,8 @@ class PWCFlow(nn.Module):
             # one pyramid pass over [img1; img2], one decoder pass over [(1,2); (2,1)]
             feats = self._feature_pyramid_extractor(torch.cat([x[:, 0:3], x[:, 3:6]], dim=0), nhwc=self._nhwc)
             p1 = feats
-            p2 = [torch.cat([f[B:], f[:B]], dim=0) for f in feats]
+            # level 0 is never read by the decoder (uflow_model.py:158): do not copy its 2B x 32 x H/2 x W/2 features
+            p2 = [None] + [torch.cat([f[B:], f[:B]], dim=0) for f in feats[1:]]
             flows = self.forward_2_frames(p1, p2, groups=2)
             res_dict['flows_fw'] = [f[:B] for f in flows]
             res_dict['flows_bw'] = [f[B:] for f in flows]

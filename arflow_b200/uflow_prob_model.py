@@ -200,7 +200,7 @@ class PWCProbFlow(nn.Module):
         for extractor in self._feature_pyramid_extractor:
             if with_bk and self._stack_directions:
                 feats = extractor(torch.cat([img1, img2], dim=0), nhwc=self._nhwc)
-                swapped = [torch.cat([f[B:], f[:B]], dim=0) for f in feats]
+                swapped = [None] + [torch.cat([f[B:], f[:B]], dim=0) for f in feats[1:]]   # level 0 is never read
                 outs = self.forward_2_frames(feats, swapped, groups=2)
                 flows_fw.append([o[:B] for o in outs])
                 flows_bw.append([o[B:] for o in outs])
