@@ -136,6 +136,16 @@ def alg_bytes(name, a):
         return a[2] * a[3] * 8
     if name == "arf_bias_leaky_nhwc_bwd":
         return a[5] * a[6] * 12
+    if name == "arf_bias_leaky_nhwc_bwd_ld":
+        return a[6] * a[7] * 12
+    if name == "arf_nhwc_unpack_add":
+        return a[2] * a[3] * a[4] * 12                     # part read + packed slice read + part write
+    if name == "arf_featnorm_fwd":
+        return a[6] * a[7] * 24                            # two maps: read twice (moments, apply), written once
+    if name == "arf_featnorm_bwd":
+        return a[9] * a[10] * 40
+    if name == "arf_pad_weight":
+        return a[6] * a[7] * a[4] * a[5] * 8
     return 0
 
 
@@ -168,9 +178,14 @@ def alg_work(name, a):
         return "N%d %dx%d->%dx%d" % (n, Hi, Wi, Ho, Wo), 0, 0
     if name in ("arf_nhwc_pack", "arf_nhwc_unpack"):
         return "N%d HW%d C%d of %d %s" % (a[2], a[3], a[4], a[5], "nhwc" if a[7] else "nchw"), 0, 0
-    if name in ("arf_bias_leaky_nhwc_fwd", "arf_bias_leaky_nhwc_bwd"):
-        rows, C = (a[2], a[3]) if name.endswith("fwd") else (a[5], a[6])
+    if name in ("arf_bias_leaky_nhwc_fwd", "arf_bias_leaky_nhwc_bwd", "arf_bias_leaky_nhwc_bwd_ld"):
+        rows, C = (a[2], a[3]) if name.endswith("fwd") else ((a[6], a[7]) if name.endswith("_ld") else (a[5], a[6]))
         return "rows%d C%d" % (rows, C), 0, 0
+    if name == "arf_nhwc_unpack_add":
+        return "N%d HW%d C%d of %d" % (a[2], a[3], a[4], a[5]), 0, 0
+    if name in ("arf_featnorm_fwd", "arf_featnorm_bwd"):
+        B, n = (a[6], a[7]) if name.endswith("fwd") else (a[9], a[10])
+        return "B%d n%d" % (B, n), 0, 0
     if name in ("arf_bias_leaky_fwd", "arf_bias_leaky_bwd"):
         B, C, HW = a[2:5] if name.endswith("fwd") else a[5:8]
         return "B%d C%d HW%d" % (B, C, HW), 0, 0
@@ -362,7 +377,8 @@ def main_b200(args):
                 q["mufu"] += mufu
             hbm, how = measured_peaks()
             # dominant = the (entry point, problem shape) with the most device time per step
-            (name, label), k = max(per_shape.items(), key=lambda kv: kv[1]["ms"])
+            (name, label), k = max(((kk, vv) for kk, vv in per_shape.items() if vv["bytes"] > 0),
+                                   key=lambda kv: kv[1]["ms"])
             ach = k["bytes"] / (k["ms"] * 1e-3) / 1e9
             traffic = None
             tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
