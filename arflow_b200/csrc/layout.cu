@@ -52,17 +52,22 @@ nhwc_part_kernel(float* __restrict__ dst, const float* __restrict__ src, long lo
 
 // NCHW part [n][c][p] <-> packed NHWC [n][p][Cd] slice, through a 32 x 32 (+1) shared-memory tile.
 // grid = (pixel tiles, channel tiles, n), block = (32, 8).
+// batch_shift: the PART's batch index is (n + batch_shift) % N — the two flow directions of a stacked batch read
+// each other's features, so the half-batch swap rides on this copy instead of a torch.cat (and, in the backward, a
+// zero-fill + slice copy + add).
 template <bool kPack>
 __global__ void __launch_bounds__(256)
-nchw_part_kernel(float* __restrict__ dst, const float* __restrict__ src, long long HW, int Cs, int Cd, int c_off) {
+nchw_part_kernel(float* __restrict__ dst, const float* __restrict__ src, long long HW, int Cs, int Cd, int c_off,
+                 int batch_shift) {
     __shared__ float tile[32][33];
     const long long p0 = (long long)blockIdx.x * 32;
     const int c0 = blockIdx.y * 32;
     const long long n = blockIdx.z;
+    const long long n_part = (n + batch_shift) % gridDim.z;
     const int tx = threadIdx.x, ty = threadIdx.y;
     if (kPack) {
         // read: lanes along pixels of one channel
-        const float* s = src + n * Cs * HW;
+        const float* s = src + n_part * Cs * HW;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int c = c0 + ty + 8 * k;
@@ -88,7 +93,7 @@ nchw_part_kernel(float* __restrict__ dst, const float* __restrict__ src, long lo
             tile[ty + 8 * k][tx] = (c < Cs && p < HW) ? __ldg(s + p * Cd + c) : 0.f;
         }
         __syncthreads();
-        float* d = dst + n * Cs * HW;
+        float* d = dst + n_part * Cs * HW;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int c = c0 + ty + 8 * k;
@@ -145,7 +150,7 @@ int launch_part(float* dst, const float* src, long long N, long long HW, int Cs,
     } else {
         if (N > 65535 || (Cs + 31) / 32 > 65535) return ARF_EINVAL;
         dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((Cs + 31) / 32), (unsigned)N);
-        nchw_part_kernel<kPack><<<grid, dim3(32, 8), 0, st>>>(dst, src, HW, Cs, Cd, c_off);
+        nchw_part_kernel<kPack><<<grid, dim3(32, 8), 0, st>>>(dst, src, HW, Cs, Cd, c_off, 0);
     }
     return ARF_OK;
 }
@@ -231,6 +236,19 @@ extern "C" int arf_nhwc_unpack(float* part, const float* packed, long long N, lo
     ARF_REQUIRE(part && packed);
     int rc = launch_part<false>(part, packed, N, HW, Cs, Cd, c_off, part_nhwc, (cudaStream_t)stream);
     if (rc) return rc;
+    ARF_CHECK_LAUNCH();
+    return ARF_OK;
+}
+
+// NCHW tensor (N,C,HW) <-> channels-last tensor (N,HW,C) with the NCHW side's batch rotated by batch_shift:
+// to_nchw = 1: nchw[(n + shift) % N] = nhwc[n];   to_nchw = 0: nhwc[n] = nchw[(n + shift) % N].
+extern "C" int arf_nhwc_transpose(float* dst, const float* src, long long N, long long HW, int C, int to_nchw,
+                                  int batch_shift, void* stream) {
+    ARF_REQUIRE(dst && src);
+    if (N <= 0 || N > 65535 || HW <= 0 || C <= 0 || (C + 31) / 32 > 65535 || batch_shift < 0) return ARF_EINVAL;
+    dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N);
+    if (to_nchw) nchw_part_kernel<false><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dst, src, HW, C, C, 0, batch_shift);
+    else nchw_part_kernel<true><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dst, src, HW, C, C, 0, batch_shift);
     ARF_CHECK_LAUNCH();
     return ARF_OK;
 }

@@ -332,14 +332,15 @@ def dense_block_nhwc(x0, convs, weights, biases, negative_slope):
 
 class _ToNchw(torch.autograd.Function):
     """channels-last -> NCHW copy (and NCHW -> channels-last for the gradient) through the tiled transpose of
-    arf_nhwc_unpack / arf_nhwc_pack: the features the NCHW hot-path kernels (warp, cost volume) read."""
+    arf_nhwc_transpose: the features the NCHW hot-path kernels (warp, cost volume) read.  out[(n + shift) % N] = x[n]."""
 
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, shift):
         B, C, H, W = x.shape
         with torch.cuda.device_of(x):
             out = torch.empty((B, C, H, W), dtype=x.dtype, device=x.device)
-            _lib.call("arf_nhwc_unpack", out.data_ptr(), x.data_ptr(), B, H * W, C, C, 0, 0, _lib.stream_ptr())
+            _lib.call("arf_nhwc_transpose", out.data_ptr(), x.data_ptr(), B, H * W, C, 1, int(shift), _lib.stream_ptr())
+        ctx.shift = int(shift)
         return out
 
     @staticmethod
@@ -348,12 +349,14 @@ class _ToNchw(torch.autograd.Function):
         B, C, H, W = g.shape
         with torch.cuda.device_of(g):
             out = torch.empty((B, C, H, W), dtype=g.dtype, device=g.device, memory_format=CL)
-            _lib.call("arf_nhwc_pack", out.data_ptr(), g.data_ptr(), B, H * W, C, C, 0, 0, _lib.stream_ptr())
-        return out
+            _lib.call("arf_nhwc_transpose", out.data_ptr(), g.data_ptr(), B, H * W, C, 0, ctx.shift, _lib.stream_ptr())
+        return out, None
 
 
-def to_nchw(x):
-    """x.contiguous() for a channels-last CUDA float32 tensor, with a coalesced transpose both ways."""
+def to_nchw(x, batch_shift=0):
+    """NCHW-contiguous copy of a channels-last CUDA float32 tensor with its batch rotated: out[(n + shift) % N] = x[n]
+    (shift = N/2 swaps the halves of a stacked two-direction batch).  Coalesced transpose both ways."""
     if not (x.is_cuda and x.dtype == torch.float32 and is_nhwc(x)):
-        return x.contiguous()
-    return _ToNchw.apply(x)
+        x = x.contiguous()
+        return torch.roll(x, batch_shift, 0) if batch_shift else x
+    return _ToNchw.apply(x, batch_shift)

@@ -292,9 +292,12 @@ class PWCFlow(nn.Module):
         context = flow = flow_up = context_up = None
         flows = []
         for level in range(self._num_levels - 1, 0, -1):
-            features1, features2 = feature_pyramid1[level], feature_pyramid2[level]     # channels-last
+            features1 = feature_pyramid1[level]                                         # channels-last
             f1 = to_nchw(features1)
-            f2 = to_nchw(features2)
+            if feature_pyramid2 is None:     # stacked directions: the other half of the same batch
+                f2 = to_nchw(features1, batch_shift=features1.shape[0] // 2)
+            else:
+                f2 = to_nchw(feature_pyramid2[level])
             warped2 = f2 if flow_up is None else ops.resample(f2, ops.flow_to_warp(flow_up))
             f1n, w2n = normalize_features([f1, warped2], normalize=self._normalize_before_cost_volume,
                                           center=self._normalize_before_cost_volume, moments_across_channels=True,
@@ -393,8 +396,11 @@ class PWCFlow(nn.Module):
             # one pyramid pass over [img1; img2], one decoder pass over [(1,2); (2,1)]
             feats = self._feature_pyramid_extractor(torch.cat([x[:, 0:3], x[:, 3:6]], dim=0), nhwc=self._nhwc)
             p1 = feats
-            # level 0 is never read by the decoder (uflow_model.py:158): do not copy its 2B x 32 x H/2 x W/2 features
-            p2 = [None] + [torch.cat([f[B:], f[:B]], dim=0) for f in feats[1:]]
+            if self._nhwc and x.is_cuda:
+                p2 = None       # the half-batch swap rides on the NHWC -> NCHW copy of the features (to_nchw)
+            else:
+                # level 0 is never read by the decoder (uflow_model.py:158): do not copy its features
+                p2 = [None] + [torch.cat([f[B:], f[:B]], dim=0) for f in feats[1:]]
             flows = self.forward_2_frames(p1, p2, groups=2)
             res_dict['flows_fw'] = [f[:B] for f in flows]
             res_dict['flows_bw'] = [f[B:] for f in flows]

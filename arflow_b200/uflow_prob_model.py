@@ -126,7 +126,8 @@ class PWCProbFlow(nn.Module):
         context = context_up = out_up = out = None
         outs = []
         for level in range(self._num_levels - 1, 0, -1):
-            features1, features2 = feature_pyramid1[level], feature_pyramid2[level]
+            features1 = feature_pyramid1[level]
+            features2 = feature_pyramid2[level] if feature_pyramid2 is not None else None
             if out_up is None:   # coarsest level: zero flow, constant log-diagonal, zero context (:265-277)
                 b, _, h, w = features1.shape
                 out_up = torch.cat([features1.new_zeros(b, L, h, w),
@@ -135,7 +136,10 @@ class PWCProbFlow(nn.Module):
 
             nhwc = self._nhwc and features1.is_cuda
             f1 = to_nchw(features1) if nhwc else features1      # NCHW copies for the hot-path kernels
-            f2 = to_nchw(features2) if nhwc else features2
+            if features2 is None:      # stacked directions (channels-last only): the other half of the same batch
+                f2 = to_nchw(features1, batch_shift=features1.shape[0] // 2)
+            else:
+                f2 = to_nchw(features2) if nhwc else features2
             cost_volumes = []
             for k in range(L // 2):
                 warped2 = ops.resample(f2, ops.flow_to_warp(out_up[:, 2 * k:2 * k + 2]))
@@ -200,7 +204,10 @@ class PWCProbFlow(nn.Module):
         for extractor in self._feature_pyramid_extractor:
             if with_bk and self._stack_directions:
                 feats = extractor(torch.cat([img1, img2], dim=0), nhwc=self._nhwc)
-                swapped = [None] + [torch.cat([f[B:], f[:B]], dim=0) for f in feats[1:]]   # level 0 is never read
+                if self._nhwc and img1.is_cuda:
+                    swapped = None     # the half-batch swap rides on the NHWC -> NCHW copy of the features
+                else:
+                    swapped = [None] + [torch.cat([f[B:], f[:B]], dim=0) for f in feats[1:]]   # level 0 is never read
                 outs = self.forward_2_frames(feats, swapped, groups=2)
                 flows_fw.append([o[:B] for o in outs])
                 flows_bw.append([o[B:] for o in outs])

@@ -377,7 +377,10 @@ def main_b200(args):
                 q["mufu"] += mufu
             hbm, how = measured_peaks()
             # dominant = the (entry point, problem shape) with the most device time per step
-            (name, label), k = max(((kk, vv) for kk, vv in per_shape.items() if vv["bytes"] > 0),
+            # (launch-latency-sized helpers such as the per-layer weight re-layout are not candidates: their event-bracketed
+            # time is mostly launch gap)
+            (name, label), k = max(((kk, vv) for kk, vv in per_shape.items()
+                                    if vv["bytes"] > 0 and kk[1] != "other" and vv["ms"] / vv["calls"] > 0.015),
                                    key=lambda kv: kv[1]["ms"])
             ach = k["bytes"] / (k["ms"] * 1e-3) / 1e9
             traffic = None

@@ -209,6 +209,11 @@ int arf_pad_weight(float* dst, const float* src, int Co, int Ci, int KH, int KW,
                    int to_padded, void* stream);
 int arf_nhwc_unpack(float* part, const float* packed, long long N, long long HW, int Cs, int Cd, int c_off,
                     int part_nhwc, void* stream);
+/* NCHW (N,C,HW) <-> channels-last (N,HW,C) copy through a tiled transpose, the NCHW side's batch index rotated by
+ * batch_shift (the stacked flow directions read each other's features: `feature_pyramid2` of uflow_model.py:255-257):
+ * to_nchw = 1: nchw[(n+shift) % N] = nhwc[n];  to_nchw = 0: nhwc[n] = nchw[(n+shift) % N]. */
+int arf_nhwc_transpose(float* dst, const float* src, long long N, long long HW, int C, int to_nchw, int batch_shift,
+                       void* stream);
 /* part (NHWC) += packed[..., c_off : c_off+Cs]: the gradient of a tensor that feeds both a convolution and the next
  * concatenation is accumulated in place instead of unpack + add */
 int arf_nhwc_unpack_add(float* part, const float* packed, long long N, long long HW, int Cs, int Cd, int c_off,
