@@ -2,7 +2,7 @@
 import torch.nn as nn
 
 from .loss_blocks import _SmoothFunction
-from .uflow_utils import (census_loss, clamp01, compute_range_map, downsample, flow_to_warp, mask_invalid, resample,
+from .uflow_utils import (census_loss, clamp01, compute_range_map, downsample, mask_invalid_flow, resample_flow,
                           upsample)
 
 
@@ -15,9 +15,9 @@ class UFlowLoss(nn.modules.Module):
 
     def _direction(self, im_a, im_b, flow_ab_0, flow_ba_2):
         """photometric term of one direction: warp im_b towards im_a, masks, fused census (uflow_loss.py:28-54)."""
-        warp_0 = flow_to_warp(flow_ab_0)
-        recons = resample(im_b.detach(), warp_0)
-        valid = mask_invalid(warp_0)
+        # resample(im_b, flow_to_warp(flow)) and mask_invalid(flow_to_warp(flow)) with the grid added in-kernel
+        recons = resample_flow(im_b.detach(), flow_ab_0)
+        valid = mask_invalid_flow(flow_ab_0)
         occu = upsample(clamp01(compute_range_map(flow_ba_2.detach())), is_flow=False, scale_factor=4.0)
         mask = (occu * valid).detach()
         return census_loss(im_a, recons, mask), mask

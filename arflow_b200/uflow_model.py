@@ -26,6 +26,7 @@ class _CudaOps:
         from . import correlation, uflow_utils
         self.flow_to_warp = uflow_utils.flow_to_warp
         self.resample = uflow_utils.resample
+        self.resample_flow = uflow_utils.resample_flow      # resample(x, flow_to_warp(flow)) in one call
         self.upsample = uflow_utils.upsample
         self.compute_cost_volume = correlation.compute_cost_volume
 
@@ -91,6 +92,12 @@ def normalize_features(feature_list, normalize, center, moments_across_channels,
     if normalize:
         feature_list = [f / s for f, s in zip(feature_list, stds)]
     return feature_list
+
+
+def warp_features(ops, features, flow):
+    """ops.resample(features, ops.flow_to_warp(flow)) (uflow_model.py:163-165); one fused call where the op set has it."""
+    fused = getattr(ops, "resample_flow", None)
+    return fused(features, flow) if fused is not None else ops.resample(features, ops.flow_to_warp(flow))
 
 
 def compute_cost_volume(features1, features2, max_displacement):
@@ -298,7 +305,7 @@ class PWCFlow(nn.Module):
                 f2 = to_nchw(features1, batch_shift=features1.shape[0] // 2)
             else:
                 f2 = to_nchw(feature_pyramid2[level])
-            warped2 = f2 if flow_up is None else ops.resample(f2, ops.flow_to_warp(flow_up))
+            warped2 = f2 if flow_up is None else warp_features(ops, f2, flow_up)
             f1n, w2n = normalize_features([f1, warped2], normalize=self._normalize_before_cost_volume,
                                           center=self._normalize_before_cost_volume, moments_across_channels=True,
                                           moments_across_images=True)
@@ -341,7 +348,7 @@ class PWCFlow(nn.Module):
             if flow_up is None:
                 warped2 = features2
             else:
-                warped2 = ops.resample(features2, ops.flow_to_warp(flow_up))
+                warped2 = warp_features(ops, features2, flow_up)
             f1n, w2n = normalize_features([features1, warped2], normalize=self._normalize_before_cost_volume,
                                           center=self._normalize_before_cost_volume, moments_across_channels=True,
                                           moments_across_images=True)

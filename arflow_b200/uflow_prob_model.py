@@ -18,7 +18,7 @@ import torch.nn.functional as func
 
 from .fused_conv import conv_bias_leaky, to_nchw
 from .uflow_model import (PWCFeaturePyramid, _CudaOps, context_up_nhwc, decoder_level_nhwc, normalize_features,
-                          refine_nhwc)
+                          refine_nhwc, warp_features)
 
 
 class PWCProbFlow(nn.Module):
@@ -142,7 +142,7 @@ class PWCProbFlow(nn.Module):
                 f2 = to_nchw(features2) if nhwc else features2
             cost_volumes = []
             for k in range(L // 2):
-                warped2 = ops.resample(f2, ops.flow_to_warp(out_up[:, 2 * k:2 * k + 2]))
+                warped2 = warp_features(ops, f2, out_up[:, 2 * k:2 * k + 2])
                 f1n, w2n = normalize_features([f1, warped2], normalize=self._normalize_before_cost_volume,
                                               center=self._normalize_before_cost_volume, moments_across_channels=True,
                                               moments_across_images=True)

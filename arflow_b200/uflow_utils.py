@@ -2,7 +2,7 @@
 import torch
 
 from . import _lib
-from .warp_utils import FIELD_COORDS, _WarpFunction  # noqa: F401
+from .warp_utils import FIELD_COORDS, FIELD_FLOW, _WarpFunction  # noqa: F401
 
 
 def flow_to_warp(flow):
@@ -20,6 +20,25 @@ def resample(source, coords):
     align_corners=True; coordinates go through the same 2*c/max(W-1,1)-1 normalisation round trip."""
     _, _, H, W = source.shape
     return _WarpFunction.apply(source, coords, max(W - 1, 1), max(H - 1, 1), FIELD_COORDS, 0, 0, True)
+
+
+def resample_flow(source, flow):
+    """resample(source, flow_to_warp(flow)) (uflow_utils.py:53-77 after :6-32) without materialising the coordinate
+    grid: the kernel adds the pixel grid to the flow itself — the same single fp32 add, so the result is bit-identical —
+    which saves the arange / cat / add kernels and their autograd counterparts on every call."""
+    _, _, H, W = source.shape
+    return _WarpFunction.apply(source, flow, max(W - 1, 1), max(H - 1, 1), FIELD_FLOW, 0, 0, True)
+
+
+def mask_invalid_flow(flow):
+    """mask_invalid(flow_to_warp(flow)) (uflow_utils.py:35-50) straight from the flow."""
+    flow = flow.detach().contiguous()
+    B, _, H, W = flow.shape
+    with torch.cuda.device_of(flow):
+        mask = torch.empty((B, 1, H, W), dtype=flow.dtype, device=flow.device)
+        _lib.call("arf_inside_mask", _lib.dev_ptr(flow, "flow"), _lib.dev_ptr(mask), B, H, W, FIELD_FLOW, 0,
+                  _lib.stream_ptr())
+    return mask
 
 
 # --------------------------------------------------------------------------- masks ---------

@@ -162,3 +162,20 @@ def test_window_flow_grad_only_full_size():
     finally:
         _variant(0)
     assert_close(g_win, g_dir, 1e-5)
+
+
+def test_resample_flow_is_resample_of_flow_to_warp():
+    """The callers' fused form (grid added in-kernel) is bit-identical to the reference's two-step form."""
+    from arflow_b200.uflow_utils import flow_to_warp, mask_invalid, mask_invalid_flow, resample, resample_flow
+    gen = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 32, 24, 40, generator=gen).cuda().requires_grad_(True)
+    f = (torch.randn(2, 2, 24, 40, generator=gen) * 4).cuda().requires_grad_(True)
+    w = torch.randn(2, 32, 24, 40, generator=gen).cuda()
+    a = resample(x, flow_to_warp(f))
+    ga = torch.autograd.grad((a * w).sum(), [x, f])
+    b = resample_flow(x, f)
+    gb = torch.autograd.grad((b * w).sum(), [x, f])
+    assert torch.equal(a, b)
+    assert_close(gb[0], ga[0], 2e-6)
+    assert torch.equal(gb[1], ga[1])
+    assert torch.equal(mask_invalid_flow(f), mask_invalid(flow_to_warp(f)))
