@@ -475,19 +475,23 @@ __device__ __forceinline__ void warp_bwd_body(float* wbuf, const float* __restri
         cp_async_wait<1>();
         __syncthreads();
         if (ps.fast) {
+            // all gy loads of the chunk are issued before the first use (CC x P independent global loads in flight)
+            float go[CC][P];
+#pragma unroll
+            for (int c = 0; c < CC; ++c) {
+                const float* gc = gyb + (size_t)(c_lo + (c < n ? c : 0)) * hwo;
+#pragma unroll
+                for (int p = 0; p < P; ++p) go[c][p] = __ldg(gc + p * rowstep);
+            }
 #pragma unroll
             for (int c = 0; c < CC; ++c) {
                 if (c < n) {
-                    const float* gc = gyb + (size_t)(c_lo + c) * hwo;
-                    float go[P];
-#pragma unroll
-                    for (int p = 0; p < P; ++p) go[p] = __ldg(gc + p * rowstep);
 #pragma unroll
                     for (int p = 0; p < P; ++p) {
                         const float* q = cur + c * S;
                         const float v0 = q[ps.o[p][0]], v1 = q[ps.o[p][1]], v2 = q[ps.o[p][2]], v3 = q[ps.o[p][3]];
-                        ax[p] = fmaf(go[p], fmaf(v3, cx[p][3], fmaf(v2, cx[p][2], fmaf(v1, cx[p][1], v0 * cx[p][0]))), ax[p]);
-                        ay[p] = fmaf(go[p], fmaf(v3, cy[p][3], fmaf(v2, cy[p][2], fmaf(v1, cy[p][1], v0 * cy[p][0]))), ay[p]);
+                        ax[p] = fmaf(go[c][p], fmaf(v3, cx[p][3], fmaf(v2, cx[p][2], fmaf(v1, cx[p][1], v0 * cx[p][0]))), ax[p]);
+                        ay[p] = fmaf(go[c][p], fmaf(v3, cy[p][3], fmaf(v2, cy[p][2], fmaf(v1, cy[p][1], v0 * cy[p][0]))), ay[p]);
                     }
                 }
             }
