@@ -205,13 +205,15 @@ warp_bwd_kernel(const float* __restrict__ x, const float* __restrict__ field,
                             go[u] = __ldg(gb + (size_t)c * hwo);
                             const float* p = xb + (size_t)c * hws;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) v[u][k] = t.in[k] ? __ldg(p + t.o[k]) : 0.f;
+                            for (int k = 0; k < 4; ++k) v[u][k] = __ldg(p + t.o[k]);   // offsets are clamped: always legal
                         }
                     }
 #pragma unroll
                     for (int u = 0; u < kCU; ++u) {
                         const int c = c0 + u * G;
                         if (c < g.C) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) v[u][k] = t.in[k] ? v[u][k] : 0.f;   // taps outside the source read as 0
                             ax = fmaf(go[u], (v[u][1] - v[u][0]) * t.fys + (v[u][3] - v[u][2]) * t.fyn, ax);
                             ay = fmaf(go[u], (v[u][2] - v[u][0]) * t.fxe + (v[u][3] - v[u][1]) * t.fxw, ay);
                             if (gx) {
