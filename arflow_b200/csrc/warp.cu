@@ -174,16 +174,18 @@ warp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ field, fl
 
 // block = (32 pixels, G channel groups); thread (px, grp) handles channels grp, grp+G, ... four at a time.
 template <int G>
-__global__ void __launch_bounds__(32 * G)
+__global__ void __launch_bounds__(G == 1 ? 128 : 32 * G)
 warp_bwd_kernel(const float* __restrict__ x, const float* __restrict__ field,
                 const float* __restrict__ gy, float* __restrict__ gx, float* __restrict__ gfield,
                 WarpGeom g) {
     __shared__ float red[2][G][32];
     const size_t hwo = (size_t)g.Ho * g.Wo, hws = (size_t)g.Hs * g.Ws;
-    const int lane = threadIdx.x, grp = threadIdx.y;
+    // G == 1 (few channels): threadIdx.y indexes independent 32-pixel runs instead of channel groups
+    const int lane = threadIdx.x, grp = G == 1 ? 0 : threadIdx.y;
+    const int rsub = G == 1 ? threadIdx.y : 0, rpb = G == 1 ? blockDim.y : 1;
     const int b = blockIdx.y;
     const long long nrun = ((long long)hwo + 31) / 32;  // 32-pixel runs per image
-    for (long long run = blockIdx.x; run < nrun; run += gridDim.x) {
+    for (long long run = (long long)blockIdx.x * rpb + rsub; run < nrun; run += (long long)gridDim.x * rpb) {
         const long long pix = run * 32 + lane;
         const bool live = pix < (long long)hwo;
         float ax = 0.f, ay = 0.f, dX = 0.f, dY = 0.f;
@@ -832,7 +834,9 @@ extern "C" int arf_warp_bwd(const float* x, const float* field, const float* gy,
     const long long cap = ((long long)ARF_NUM_SMS * 32 + B - 1) / B;
     dim3 grid((unsigned)(runs < cap ? runs : cap), B);
     if (C <= 4) {
-        warp_bwd_kernel<1><<<grid, dim3(32, 1), 0, st>>>(x, field, gy, gx, gfield, g);
+        const long long blocks = (runs + 3) / 4;
+        grid.x = (unsigned)(blocks < 2 * cap ? blocks : 2 * cap);
+        warp_bwd_kernel<1><<<grid, dim3(32, 4), 0, st>>>(x, field, gy, gx, gfield, g);
     } else if (C <= 16) {
         warp_bwd_kernel<4><<<grid, dim3(32, 4), 0, st>>>(x, field, gy, gx, gfield, g);
     } else {
