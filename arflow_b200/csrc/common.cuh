@@ -59,3 +59,19 @@ __device__ __forceinline__ float arf_ldg_stream(const float* p) {
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
+
+// idx -> (x, y, b) for a (B, H, W) index space.  Indices below 2^32 (every shape the networks use) take 32-bit
+// divisions; a 64-bit div/mod pair per element costs more than the rest of an elementwise kernel.
+__device__ __forceinline__ void arf_split3(long long idx, int W, int H, int& x, int& y, int& b) {
+    if (idx <= 0xffffffffLL) {
+        const unsigned u = (unsigned)idx, t = u / (unsigned)W, bb = t / (unsigned)H;
+        x = (int)(u - t * (unsigned)W);
+        y = (int)(t - bb * (unsigned)H);
+        b = (int)bb;
+    } else {
+        const long long t = idx / W;
+        x = (int)(idx - t * W);
+        y = (int)(t % H);
+        b = (int)(t / H);
+    }
+}

@@ -22,9 +22,8 @@ __global__ void inside_mask_kernel(const float* __restrict__ field, float* __res
     long long total = (long long)B * H * W;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        int j = idx % W;
-        long long t = idx / W;
-        int i = t % H, b = t / H;
+        int j, i, b;
+        arf_split3(idx, W, H, j, i, b);
         float x, y;
         field_xy(field, kind, b, i, j, H, W, x, y);
         float mw = (float)(W - 1), mh = (float)(H - 1);
@@ -41,9 +40,8 @@ __global__ void range_map_kernel(const float* __restrict__ field, float* __restr
     long long total = (long long)B * H * W;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        int j = idx % W;
-        long long t = idx / W;
-        int i = t % H, b = t / H;
+        int j, i, b;
+        arf_split3(idx, W, H, j, i, b);
         float x, y;
         field_xy(field, kind, b, i, j, H, W, x, y);
         float xf = floorf(x), yf = floorf(y);
@@ -74,9 +72,8 @@ __global__ void range_map_bwd_kernel(const float* __restrict__ field, const floa
     const size_t hw = (size_t)H * W;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        int j = idx % W;
-        long long t = idx / W;
-        int i = t % H, b = t / H;
+        int j, i, b;
+        arf_split3(idx, W, H, j, i, b);
         float x, y;
         field_xy(field, kind, b, i, j, H, W, x, y);
         float xf = floorf(x), yf = floorf(y);

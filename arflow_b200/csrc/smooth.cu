@@ -50,9 +50,8 @@ smooth_fwd_kernel(const float* __restrict__ img, const float* __restrict__ flow,
     float sx = 0.f, sy = 0.f;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        int x = idx % g.W;
-        long long t = idx / g.W;
-        int y = t % g.H, b = t / g.H;
+        int x, y, b;
+        arf_split3(idx, g.W, g.H, x, y, b);
         size_t o = (size_t)y * g.W + x;
         const float* fb = flow + (size_t)b * 2 * hw;
         if (x < g.W - g.order) {
@@ -101,9 +100,8 @@ smooth_bwd_kernel(const float* __restrict__ img, const float* __restrict__ flow,
     const float gl = __ldg(gloss) * g.final_scale;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        int x = idx % g.W;
-        long long t = idx / g.W;
-        int y = t % g.H, b = t / g.H;
+        int x, y, b;
+        arf_split3(idx, g.W, g.H, x, y, b);
         const float* fb = flow + (size_t)b * 2 * hw;
         float gx0 = 0.f, gx1 = 0.f, gy0 = 0.f, gy1 = 0.f;
         // term starting at xt = x-k has coefficient coef[k] on f[x]:  order 1: {-1,+1}   order 2: {+1,-2,+1}

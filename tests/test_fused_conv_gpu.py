@@ -91,7 +91,7 @@ def test_nhwc_concat_matches_torch_cat(B, H, W):
     out, n = nhwc_concat(parts)
     assert n == 147 and out.shape == (B, 152, H, W) and is_nhwc(out)
     ref = torch.cat([p.detach() for p in parts], dim=1)
-    assert torch.equal(out[:, :147], ref) and float(out[:, 147:].abs().max()) == 0.0
+    assert torch.equal(out.detach()[:, :147], ref) and float(out.detach()[:, 147:].abs().max()) == 0.0
     w = torch.randn(out.shape, generator=gen).cuda()
     grads = torch.autograd.grad((out * w).sum(), parts)
     off = 0

@@ -113,5 +113,12 @@ def test_channels_last_and_nchw_networks_agree_with_gradients():
     assert_close(res[1][0], res[0][0], 1e-4, "flows[2]")
     assert_close(res[1][1], res[0][1], 1e-5, "loss")
     assert res[0][2].keys() == res[1][2].keys()
+    # The two runs use different cuDNN algorithms and both contain atomics (warp source gradient, split-K wgrad), and
+    # the network amplifies such last-bit differences through flow -> warp -> cost volume; individual parameters are
+    # therefore held to 2e-2 of their largest gradient entry, the gradient as a whole to 2e-3 in L2.
+    num = den = 0.0
     for n in res[0][2]:
-        assert_close(res[1][2][n], res[0][2][n], 5e-3, "grad " + n)
+        assert_close(res[1][2][n], res[0][2][n], 2e-2, "grad " + n)
+        num += float((res[1][2][n].double() - res[0][2][n].double()).square().sum())
+        den += float(res[0][2][n].double().square().sum())
+    assert (num / den) ** 0.5 < 2e-3, (num / den) ** 0.5

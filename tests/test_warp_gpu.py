@@ -126,7 +126,7 @@ def test_window_kernels_vs_oracle_and_direct(oracle, shape, sigma, shift, pad, a
     assert_close(out, ref, RTOL_VALUE)
     assert_close(gx, rx, RTOL_GRAD)
     assert_close(gf, rf, RTOL_GRAD)
-    assert_close(gx, gx_d, 2e-6)
+    assert_close(gx, gx_d, 1e-5)      # same sums in a different (atomic) order
     assert_close(gf, gf_d, 1e-5)
 
 
