@@ -308,7 +308,9 @@ corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ C
 //   * register tilings that read operands with LDS.128 along x (12 px x 9 dx per thread): 118-148 us for the loop;
 //   * packed FFMA2 (32 FFMA2 + 8 FFMA instead of 72 FFMA per channel, broadcast operand, no MOVs, identical bits):
 //     163 us with one channel in flight, 149 us with two (kUnroll = 2) - the default now, 2.5% over scalar;
-//   * 6 stages of 4 channels instead of 3 of 8: 153-157 us; two row groups per CTA (1 CTA/SM): slower.
+//   * 6 stages of 4 channels instead of 3 of 8: 153-157 us; two row groups per CTA (1 CTA/SM): slower;
+//   * the same FFMA2 packing in the backward kernels (40 FFMA2 per channel with zero-padded edge pairs, bit-identical):
+//     398 vs 345 us for both gradients - dropped.
 // Getting further needs fewer shared-memory operands per FMA than a 72-accumulator thread tile allows (bigger tiles
 // do not fit two CTAs per SM) or the tensor pipe, which cannot meet the 1e-5 parity bar.
 
