@@ -1,20 +1,22 @@
 #!/bin/bash
 # ncu --set full captures of the hot kernels (one launch each, after a plain run of the same command).
-# usage: tools/profile_kernels.sh <tag>      (run under gpurun; reports land in gpurun_out/)
+# usage: tools/profile_kernels.sh <tag> [names...]     (run under gpurun; reports land in gpurun_out/)
 set -u
 TAG=${1:-r1}
+shift || true
+ONLY="$*"
 OUT=gpurun_out
 mkdir -p $OUT
 prof () {  # name kernel-regex microbench-args...
   local name=$1; local regex=$2; shift 2
+  if [ -n "$ONLY" ] && ! echo " $ONLY " | grep -q " $name "; then return; fi
   python tools/microbench.py "$@" > $OUT/plain_${name}.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:$regex -s 3 -c 1 \
       -o $OUT/${name}_${TAG} -f python tools/microbench.py "$@" > $OUT/ncu_${name}.log 2>&1
   tail -1 $OUT/plain_${name}.log
 }
 prof corr_fwd corr_fwd_md4 corr_fwd --shapes 64x32x96x128
-prof corr_bwd1 'corr_bwd_md4<\(bool\)0' corr_bwd --shapes 64x32x96x128
-prof corr_bwd2 'corr_bwd_md4<\(bool\)1' corr_bwd --shapes 64x32x96x128
+prof corr_bwd corr_bwd_md4 corr_bwd --shapes 64x32x96x128
 prof warp_fwd warp_fwd_kernel warp --flow smooth --shapes 64x32x96x128
 prof warp_gfield warp_gfield_win warp --flow smooth --shapes 64x32x96x128
 prof warp_gx warp_gx_csr warp --flow smooth --shapes 64x32x96x128
@@ -23,4 +25,7 @@ prof census_fwd census_fwd_kernel census --shapes 8x3x384x512
 prof census_bwd census_bwd_kernel census --shapes 8x3x384x512
 prof stencil_fwd 'stencil_mv_kernel' stencil
 prof stencil_bwd 'stencil_mv_bwd_kernel' stencil
+prof epilogue_fwd bias_leaky_nhwc_fwd_kernel glue
+prof epilogue_bwd bias_leaky_nhwc_bwd_kernel glue
+prof nhwc_pack nhwc_part_kernel glue
 ls -la $OUT/*_${TAG}.ncu-rep
