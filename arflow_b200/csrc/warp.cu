@@ -726,15 +726,17 @@ warp_gx_csr(const float* __restrict__ field, const float* __restrict__ gy, float
 
 constexpr size_t kWinSmem = 2 * kWCap * sizeof(float);
 
-// The window kernels pay their per-tile set-up (tap geometry, bounding box, CSR sort) off once there are many
-// channels and enough tiles to fill the machine several times; smaller problems stay on the direct kernels.
-// Measured on B200 (tools/microbench.py warp): 64x32x96x128 flow gradient 209 -> 107 us, both gradients 465 -> 313 us;
-// at 8x32x96x128 the direct kernels win (32 vs 42 us, 65 vs 94 us).  The forward gains nothing from staging
-// (74 vs 76 us) and always runs direct.
-inline bool use_window(const WarpGeom& g, int variant) {
+// Routing, measured on B200 (tools/microbench.py warp --warp-variant 1|2, smooth flow, C = 32):
+//   flow gradient only:   window wins at every size that fills tiles (16x32x48x64: 10.9 vs 13.5 us, 8x32x96x128: 19.7 vs
+//                         24.4, 16x32x96x128: 30.2 vs 44.9, 64x32x96x128: 75 vs 206);
+//   both gradients:       window + CSR needs a large problem to pay for its per-tile sort (32x32x96x128: 126 vs 133 us,
+//                         64x32x96x128: 222 vs 314; 16x32x96x128: 81 vs 71, 8x32x96x128: 53 vs 38 -> direct).
+// The forward gains nothing from staging (74 vs 76 us) and always runs direct.
+inline bool use_window(const WarpGeom& g, int variant, bool want_gx) {
     if (g.interp != ARF_INTERP_BILINEAR || (size_t)g.Hs * g.Ws >= 0x7fffffffu) return false;
     if (variant == 2) return true;                        // test hook: force
-    return g.C >= 8 && g.Wo >= 48 && g.Ho >= 12 && (long long)g.B * g.Ho * g.Wo >= 400000LL;
+    if (!(g.C >= 8 && g.Wo >= 48 && g.Ho >= 12)) return false;
+    return !want_gx || (long long)g.B * g.Ho * g.Wo >= 350000LL;
 }
 // rows per tile = 4P: the tallest tile that still gives every SM a few CTAs
 inline int window_p(const WarpGeom& g) {
@@ -794,7 +796,7 @@ extern "C" int arf_warp_bwd(const float* x, const float* field, const float* gy,
     }
     if (!gx && !gfield) return ARF_OK;
     if (B > 65535) return ARF_EINVAL;
-    if (g_warp_variant != 1 && use_window(g, g_warp_variant)) {
+    if (g_warp_variant != 1 && use_window(g, g_warp_variant, gx != nullptr)) {
         const int P = window_p(g);
         const int tiles_x = arf_cdiv(Wo, kWTW), tiles_y = arf_cdiv(Ho, 4 * P);
         const long long ntiles = (long long)tiles_x * tiles_y * B;
