@@ -167,7 +167,7 @@ __device__ __forceinline__ void pair_grads(float da, float db, float gsum, float
 }
 
 template <int R, bool kA, bool kB>
-__global__ void __launch_bounds__(kCThreads, 3)
+__global__ void __launch_bounds__(kCThreads, 6)
 census_bwd_kernel(const float* __restrict__ im_a, const float* __restrict__ im_b, const float* __restrict__ ghamming,
                   const float* __restrict__ hamming, const float* __restrict__ mask, const float* __restrict__ sums,
                   const float* __restrict__ gloss, float* __restrict__ g_a, float* __restrict__ g_b, int B, int H,
