@@ -48,7 +48,8 @@ PROTOTYPES = {
     "arf_bias_leaky_nhwc_num_partials": [ctypes.c_longlong, c_int],
     "arf_bias_leaky_nhwc_fwd": [_P, _P, ctypes.c_longlong, c_int, c_float, _P],
     "arf_bias_leaky_nhwc_bwd": [_P, _P, _P, _P, _P, ctypes.c_longlong, c_int, c_float, _P],
-    "arf_bias_leaky_nhwc_bwd_ld": [_P, ctypes.c_longlong, _P, _P, _P, _P, ctypes.c_longlong, c_int, c_float, _P],
+    "arf_bias_leaky_nhwc_bwd_ld": [_P, ctypes.c_longlong, _P, ctypes.c_longlong, _P, _P, _P, ctypes.c_longlong, c_int, c_float, _P],
+    "arf_bias_leaky_nhwc_fwd_ld": [_P, _P, ctypes.c_longlong, _P, ctypes.c_longlong, c_int, c_float, _P],
     "arf_nhwc_unpack_add": [_P, _P, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, c_int, _P],
     "arf_pad_weight": [_P, _P] + [c_int] * 6 + [ctypes.c_longlong] * 4 + [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, _P],
     "arf_nhwc_transpose": [_P, _P, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, c_int, _P],

@@ -97,22 +97,29 @@ inline int nchunks_of(long long HW) { return (int)((HW + kEChunk - 1) / kEChunk)
 constexpr int kERows = 256;       // rows of the matrix handled by one CTA of the backward
 
 __global__ void __launch_bounds__(kEThreads)
-bias_leaky_nhwc_fwd_kernel(float* __restrict__ y, const float* __restrict__ bias, long long total, int C, float slope, int vec) {
+bias_leaky_nhwc_fwd_kernel(const float* src, float* dst, long long dst_ld, const float* __restrict__ bias, long long total,
+                           int C, float slope, int vec) {
+    // src: packed rows x C (the convolution output); dst: the same matrix (in place) or a column slice of a wider
+    // row-major matrix with row stride dst_ld (the next dense-block input: no separate concat copy of this part)
     if (vec) {
         for (long long e = 4 * (blockIdx.x * (long long)kEThreads + threadIdx.x); e < total; e += 4LL * gridDim.x * kEThreads) {
-            float4 v = *reinterpret_cast<float4*>(y + e);
+            float4 v = *reinterpret_cast<const float4*>(src + e);
+            const long long r = e / C;
+            const int c = (int)(e - r * C);
             if (bias) {
-                const float4 b = *reinterpret_cast<const float4*>(bias + (int)(e % C));
+                const float4 b = *reinterpret_cast<const float4*>(bias + c);
                 v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
             }
             v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
             v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
-            *reinterpret_cast<float4*>(y + e) = v;
+            *reinterpret_cast<float4*>(dst + r * dst_ld + c) = v;
         }
     } else {
         for (long long e = blockIdx.x * (long long)kEThreads + threadIdx.x; e < total; e += (long long)gridDim.x * kEThreads) {
-            float v = y[e] + (bias ? __ldg(bias + (int)(e % C)) : 0.f);
-            y[e] = v > 0.f ? v : v * slope;
+            const long long r = e / C;
+            const int c = (int)(e - r * C);
+            float v = src[e] + (bias ? __ldg(bias + c) : 0.f);
+            dst[r * dst_ld + c] = v > 0.f ? v : v * slope;
         }
     }
 }
@@ -121,8 +128,8 @@ bias_leaky_nhwc_fwd_kernel(float* __restrict__ y, const float* __restrict__ bias
 // rows t / G, t / G + 256 / G, ...; the per-thread column sums are reduced through shared memory, one partial row
 // of C sums per CTA.
 __global__ void __launch_bounds__(kEThreads)
-bias_leaky_nhwc_bwd_kernel(const float* __restrict__ gy, long long gy_ld, const float* __restrict__ y, float* __restrict__ g,
-                           float* __restrict__ partials, long long rows, int C, float slope, int vec) {
+bias_leaky_nhwc_bwd_kernel(const float* __restrict__ gy, long long gy_ld, const float* __restrict__ y, long long y_ld,
+                           float* __restrict__ g, float* __restrict__ partials, long long rows, int C, float slope, int vec) {
     extern __shared__ float sacc[];          // kEThreads * 4 floats
     const long long r0 = (long long)blockIdx.x * kERows;
     const long long r1 = r0 + kERows < rows ? r0 + kERows : rows;
@@ -135,10 +142,11 @@ bias_leaky_nhwc_bwd_kernel(const float* __restrict__ gy, long long gy_ld, const 
         const int cg = threadIdx.x % G, rstep = kEThreads / G;      // threads >= rstep * G stay idle (G = 24: 240 of 256)
         for (long long r = r0 + threadIdx.x / G; r < r1 && threadIdx.x < rstep * G; r += rstep) {
             const long long e = r * C + (long long)cg * w;
-            const long long eg = r * gy_ld + (long long)cg * w;     // gy may be a column slice of a wider matrix
+            const long long eg = r * gy_ld + (long long)cg * w;     // gy and y may be column slices of wider matrices
+            const long long ey = r * y_ld + (long long)cg * w;
             if (vec) {
                 const float4 a = *reinterpret_cast<const float4*>(gy + eg);
-                const float4 b = *reinterpret_cast<const float4*>(y + e);
+                const float4 b = *reinterpret_cast<const float4*>(y + ey);
                 float4 o;
                 o.x = b.x > 0.f ? a.x : a.x * slope; o.y = b.y > 0.f ? a.y : a.y * slope;
                 o.z = b.z > 0.f ? a.z : a.z * slope; o.w = b.w > 0.f ? a.w : a.w * slope;
@@ -146,7 +154,7 @@ bias_leaky_nhwc_bwd_kernel(const float* __restrict__ gy, long long gy_ld, const 
                 acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
             } else {
                 const float a = gy[eg];
-                const float o = y[e] > 0.f ? a : a * slope;
+                const float o = y[ey] > 0.f ? a : a * slope;
                 g[e] = o;
                 acc.x += o;
             }
@@ -167,7 +175,7 @@ bias_leaky_nhwc_bwd_kernel(const float* __restrict__ gy, long long gy_ld, const 
         for (long long e = r0 * C + threadIdx.x; e < r1 * C; e += kEThreads) {
             const long long r = e / C;
             const float a = gy[r * gy_ld + (e - r * C)];
-            g[e] = y[e] > 0.f ? a : a * slope;
+            g[e] = y[r * y_ld + (e - r * C)] > 0.f ? a : a * slope;
         }
         if (partials) {
             __syncthreads();
@@ -207,33 +215,39 @@ extern "C" long long arf_bias_leaky_nhwc_num_partials(long long rows, int C) {
 }
 
 extern "C" int arf_bias_leaky_nhwc_fwd(float* y, const float* bias, long long rows, int C, float slope, void* stream) {
-    ARF_REQUIRE(y);
-    ARF_REQUIRE(rows > 0 && C > 0);
-    const int vec = ((uintptr_t)y % 16 == 0) && (C % 4 == 0) && (!bias || (uintptr_t)bias % 16 == 0);
+    return arf_bias_leaky_nhwc_fwd_ld(y, y, C, bias, rows, C, slope, stream);
+}
+
+extern "C" int arf_bias_leaky_nhwc_fwd_ld(const float* src, float* dst, long long dst_ld, const float* bias, long long rows,
+                                          int C, float slope, void* stream) {
+    ARF_REQUIRE(src && dst);
+    ARF_REQUIRE(rows > 0 && C > 0 && dst_ld >= C);
+    const int vec = ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0) && (C % 4 == 0) && (dst_ld % 4 == 0) &&
+                    (!bias || (uintptr_t)bias % 16 == 0);
     const long long total = rows * C;
     bias_leaky_nhwc_fwd_kernel<<<arf_grid_1d(vec ? total / 4 : total, kEThreads, 16), kEThreads, 0, (cudaStream_t)stream>>>(
-        y, bias, total, C, slope, vec);
+        src, dst, dst_ld, bias, total, C, slope, vec);
     ARF_CHECK_LAUNCH();
     return ARF_OK;
 }
 
 extern "C" int arf_bias_leaky_nhwc_bwd(const float* gy, const float* y, float* g, float* partials, float* dbias,
                                        long long rows, int C, float slope, void* stream) {
-    return arf_bias_leaky_nhwc_bwd_ld(gy, C, y, g, partials, dbias, rows, C, slope, stream);
+    return arf_bias_leaky_nhwc_bwd_ld(gy, C, y, C, g, partials, dbias, rows, C, slope, stream);
 }
 
-extern "C" int arf_bias_leaky_nhwc_bwd_ld(const float* gy, long long gy_ld, const float* y, float* g, float* partials,
-                                          float* dbias, long long rows, int C, float slope, void* stream) {
+extern "C" int arf_bias_leaky_nhwc_bwd_ld(const float* gy, long long gy_ld, const float* y, long long y_ld, float* g,
+                                          float* partials, float* dbias, long long rows, int C, float slope, void* stream) {
     ARF_REQUIRE(gy && y && g);
-    ARF_REQUIRE(rows > 0 && C > 0 && gy_ld >= C);
+    ARF_REQUIRE(rows > 0 && C > 0 && gy_ld >= C && y_ld >= C);
     if (dbias) ARF_REQUIRE(partials != nullptr);
     const long long nblk = (rows + kERows - 1) / kERows;
     if (nblk > 0x7fffffffLL) return ARF_EINVAL;
     const int vec = ((uintptr_t)gy % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)g % 16 == 0) && (C % 4 == 0) &&
-                    (gy_ld % 4 == 0);
+                    (gy_ld % 4 == 0) && (y_ld % 4 == 0);
     cudaStream_t st = (cudaStream_t)stream;
     bias_leaky_nhwc_bwd_kernel<<<(unsigned)nblk, kEThreads, kEThreads * 4 * sizeof(float), st>>>(
-        gy, gy_ld, y, g, dbias ? partials : nullptr, rows, C, slope, vec);
+        gy, gy_ld, y, y_ld, g, dbias ? partials : nullptr, rows, C, slope, vec);
     ARF_CHECK_LAUNCH();
     if (dbias) {
         bias_grad_nhwc_finalize_kernel<<<arf_cdiv(C, 32), dim3(32, 32), 0, st>>>(partials, dbias, nblk, C);

@@ -247,7 +247,8 @@ class _DenseBlockNhwc(torch.autograd.Function):
     """The PWC decoder's dense block (models/uflow_model.py:195-198) on packed channels-last tensors, with a manual
     backward:   x_{i+1} = cat([x_i, leaky(conv_i(x_i) + b_i)]),   returns the last layer's output.
 
-    Forward = what conv_bias_leaky + nhwc_concat do layer by layer.  The backward walks the layers in reverse and
+    Forward = what conv_bias_leaky + nhwc_concat do layer by layer, except that a layer's activated output is written
+    straight into its column slice of the next input.  The backward walks the layers in reverse and
     keeps ONE running gradient G (w.r.t. x_{i+1}): a layer's output gradient is read straight out of G's column
     slice by the fused epilogue backward (no unpack copy), and the part of G that belongs to x_i is accumulated
     into the convolution's input gradient in place (arf_nhwc_unpack_add) — instead of autograd's unpack copy of
@@ -257,35 +258,39 @@ class _DenseBlockNhwc(torch.autograd.Function):
     def forward(ctx, slope, geom, x0, *wb):
         n = len(wb) // 2
         ws, bs = wb[:n], wb[n:]
-        xs, ys = [x0], []
+        xs, widths = [x0], []
         x = x0
         B, _, H, W = x0.shape
         rows = B * H * W
+        y = None
         for i in range(n):
             stride, padding, dilation = geom[i]
             y = func.conv2d(x, ws[i], None, stride, padding, dilation).contiguous(memory_format=CL)
             C = y.shape[1]
+            widths.append(C)
+            bptr = bs[i].contiguous().data_ptr() if bs[i] is not None else None
             with torch.cuda.device_of(y):
-                _lib.call("arf_bias_leaky_nhwc_fwd", y.data_ptr(),
-                          bs[i].contiguous().data_ptr() if bs[i] is not None else None, rows, C, float(slope),
-                          _lib.stream_ptr())
-                ys.append(y)
                 if i + 1 < n:
+                    # next input = [x | leaky(conv + b)]: the prefix is copied, the activated output is written straight
+                    # into its column slice (it is read from there again in the backward; no separate copy of it exists)
                     cin = x.shape[1]
                     nx = torch.empty((B, cin + C, H, W), dtype=x.dtype, device=x.device, memory_format=CL)
                     _lib.call("arf_nhwc_pack", nx.data_ptr(), x.data_ptr(), B, H * W, cin, cin + C, 0, 1, _lib.stream_ptr())
-                    _lib.call("arf_nhwc_pack", nx.data_ptr(), y.data_ptr(), B, H * W, C, cin + C, cin, 1, _lib.stream_ptr())
+                    _lib.call("arf_bias_leaky_nhwc_fwd_ld", y.data_ptr(), nx.data_ptr() + 4 * cin, cin + C, bptr, rows, C,
+                              float(slope), _lib.stream_ptr())
                     x = nx
                     xs.append(x)
-        ctx.save_for_backward(*xs, *ys, *ws)
-        ctx.cfg = (n, float(slope), geom, [b is not None for b in bs])
-        return ys[-1]
+                else:
+                    _lib.call("arf_bias_leaky_nhwc_fwd", y.data_ptr(), bptr, rows, C, float(slope), _lib.stream_ptr())
+        ctx.save_for_backward(*xs, y, *ws)
+        ctx.cfg = (n, float(slope), geom, [b is not None for b in bs], widths)
+        return y
 
     @staticmethod
     def backward(ctx, gy_last):
-        n, slope, geom, has_bias = ctx.cfg
+        n, slope, geom, has_bias, widths = ctx.cfg
         saved = ctx.saved_tensors
-        xs, ys, ws = saved[:n], saved[n:2 * n], saved[2 * n:3 * n]
+        xs, y_last, ws = saved[:n], saved[n], saved[n + 1:2 * n + 1]
         lib = _lib.load()
         B, _, H, W = xs[0].shape
         rows = B * H * W
@@ -293,19 +298,20 @@ class _DenseBlockNhwc(torch.autograd.Function):
         G = None            # gradient w.r.t. xs[i + 1] (packed, width = xs[i + 1].shape[1])
         with torch.cuda.device_of(xs[0]):
             for i in range(n - 1, -1, -1):
-                y = ys[i]
-                C, cin = y.shape[1], xs[i].shape[1]
+                C, cin = widths[i], xs[i].shape[1]
                 if G is None:
                     gy = gy_last.contiguous(memory_format=CL)
                     gy_ptr, gy_ld = gy.data_ptr(), C
+                    y_ptr, y_ld = y_last.data_ptr(), C
                 else:
-                    gy_ptr, gy_ld = G.data_ptr() + 4 * cin, G.shape[1]      # columns [cin, cin + C) of G
+                    gy_ptr, gy_ld = G.data_ptr() + 4 * cin, G.shape[1]              # columns [cin, cin + C) of G
+                    y_ptr, y_ld = xs[i + 1].data_ptr() + 4 * cin, xs[i + 1].shape[1]   # ... and of the next input
                 need_b = has_bias[i] and ctx.needs_input_grad[3 + n + i]
-                g = torch.empty_like(y)
-                db = torch.empty(C, dtype=y.dtype, device=y.device) if need_b else None
-                part = (torch.empty(lib.arf_bias_leaky_nhwc_num_partials(rows, C), dtype=y.dtype, device=y.device)
+                g = torch.empty((B, C, H, W), dtype=xs[0].dtype, device=xs[0].device, memory_format=CL)
+                db = torch.empty(C, dtype=g.dtype, device=g.device) if need_b else None
+                part = (torch.empty(lib.arf_bias_leaky_nhwc_num_partials(rows, C), dtype=g.dtype, device=g.device)
                         if need_b else None)
-                _lib.call("arf_bias_leaky_nhwc_bwd_ld", gy_ptr, gy_ld, y.data_ptr(), g.data_ptr(),
+                _lib.call("arf_bias_leaky_nhwc_bwd_ld", gy_ptr, gy_ld, y_ptr, y_ld, g.data_ptr(),
                           part.data_ptr() if need_b else None, db.data_ptr() if need_b else None, rows, C, slope,
                           _lib.stream_ptr())
                 stride, padding, dilation = geom[i]

@@ -137,7 +137,9 @@ def alg_bytes(name, a):
     if name == "arf_bias_leaky_nhwc_bwd":
         return a[5] * a[6] * 12
     if name == "arf_bias_leaky_nhwc_bwd_ld":
-        return a[6] * a[7] * 12
+        return a[7] * a[8] * 12
+    if name == "arf_bias_leaky_nhwc_fwd_ld":
+        return a[4] * a[5] * 8
     if name == "arf_nhwc_unpack_add":
         return a[2] * a[3] * a[4] * 12                     # part read + packed slice read + part write
     if name == "arf_featnorm_fwd":
@@ -178,8 +180,11 @@ def alg_work(name, a):
         return "N%d %dx%d->%dx%d" % (n, Hi, Wi, Ho, Wo), 0, 0
     if name in ("arf_nhwc_pack", "arf_nhwc_unpack"):
         return "N%d HW%d C%d of %d %s" % (a[2], a[3], a[4], a[5], "nhwc" if a[7] else "nchw"), 0, 0
-    if name in ("arf_bias_leaky_nhwc_fwd", "arf_bias_leaky_nhwc_bwd", "arf_bias_leaky_nhwc_bwd_ld"):
-        rows, C = (a[2], a[3]) if name.endswith("fwd") else ((a[6], a[7]) if name.endswith("_ld") else (a[5], a[6]))
+    if name in ("arf_bias_leaky_nhwc_fwd", "arf_bias_leaky_nhwc_bwd", "arf_bias_leaky_nhwc_bwd_ld",
+                "arf_bias_leaky_nhwc_fwd_ld"):
+        i = {"arf_bias_leaky_nhwc_fwd": 2, "arf_bias_leaky_nhwc_bwd": 5, "arf_bias_leaky_nhwc_bwd_ld": 7,
+             "arf_bias_leaky_nhwc_fwd_ld": 4}[name]
+        rows, C = a[i], a[i + 1]
         return "rows%d C%d" % (rows, C), 0, 0
     if name == "arf_nhwc_unpack_add":
         return "N%d HW%d C%d of %d" % (a[2], a[3], a[4], a[5]), 0, 0

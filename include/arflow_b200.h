@@ -189,10 +189,15 @@ long long arf_bias_leaky_nhwc_num_partials(long long rows, int C);
 int arf_bias_leaky_nhwc_fwd(float* y, const float* bias, long long rows, int C, float slope, void* stream);
 int arf_bias_leaky_nhwc_bwd(const float* gy, const float* y, float* g, float* partials, float* dbias, long long rows,
                             int C, float slope, void* stream);
-/* same, with gy a column slice of a wider row-major matrix: row stride gy_ld >= C (the dense block's backward reads
- * a layer's output gradient straight out of the gradient of the concatenation it went into) */
-int arf_bias_leaky_nhwc_bwd_ld(const float* gy, long long gy_ld, const float* y, float* g, float* partials, float* dbias,
-                               long long rows, int C, float slope, void* stream);
+/* same, with gy and y column slices of wider row-major matrices (row strides gy_ld, y_ld >= C): the dense block's
+ * backward reads a layer's output gradient straight out of the gradient of the concatenation it went into, and the
+ * layer's activated output out of that concatenation itself */
+int arf_bias_leaky_nhwc_bwd_ld(const float* gy, long long gy_ld, const float* y, long long y_ld, float* g, float* partials,
+                               float* dbias, long long rows, int C, float slope, void* stream);
+/* forward with a separate destination: dst[r*dst_ld + c] = leaky(src[r*C + c] + bias[c]) — the activated output lands
+ * directly in its column slice of the next dense-block input (dst_ld = that input's width) */
+int arf_bias_leaky_nhwc_fwd_ld(const float* src, float* dst, long long dst_ld, const float* bias, long long rows, int C,
+                               float slope, void* stream);
 
 /* ---------------------------------------------------------------- NHWC concat ---------- */
 /* The decoder's torch.cat([...], dim=1) (models/uflow_model.py:189-205) into a packed NHWC tensor of Cd channels
