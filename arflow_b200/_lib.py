@@ -53,6 +53,8 @@ PROTOTYPES = {
     "arf_nhwc_unpack_add": [_P, _P, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, c_int, _P],
     "arf_pad_weight": [_P, _P] + [c_int] * 6 + [ctypes.c_longlong] * 4 + [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, _P],
     "arf_nhwc_transpose": [_P, _P, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, c_int, _P],
+    "arf_nhwc_pack_act": [_P, _P, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, c_int, c_float, _P],
+    "arf_nhwc_unpack_act": [_P, _P, _P, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, c_int, c_float, _P],
     "arf_nhwc_pack": [_P, _P, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, c_int, c_int, _P],
     "arf_nhwc_unpack": [_P, _P, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, c_int, c_int, _P],
     "arf_stencil_mv_fwd": [_P, _P, _P] + [c_int] * 5 + [_P],

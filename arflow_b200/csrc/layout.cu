@@ -55,10 +55,12 @@ nhwc_part_kernel(float* __restrict__ dst, const float* __restrict__ src, long lo
 // batch_shift: the PART's batch index is (n + batch_shift) % N — the two flow directions of a stacked batch read
 // each other's features, so the half-batch swap rides on this copy instead of a torch.cat (and, in the backward, a
 // zero-fill + slice copy + add).
+// slope != 1: a leaky ReLU rides on the copy (the cost volume's activation, models/uflow_model.py:185-186): pack writes
+// leaky(src); unpack returns grad * (fwd > 0 ? 1 : slope) with fwd = the packed forward tensor (same addressing).
 template <bool kPack>
 __global__ void __launch_bounds__(256)
 nchw_part_kernel(float* __restrict__ dst, const float* __restrict__ src, long long HW, int Cs, int Cd, int c_off,
-                 int batch_shift) {
+                 int batch_shift, float slope = 1.f, const float* __restrict__ fwd = nullptr) {
     __shared__ float tile[32][33];
     const long long p0 = (long long)blockIdx.x * 32;
     const int c0 = blockIdx.y * 32;
@@ -72,7 +74,8 @@ nchw_part_kernel(float* __restrict__ dst, const float* __restrict__ src, long lo
         for (int k = 0; k < 4; ++k) {
             const int c = c0 + ty + 8 * k;
             const long long p = p0 + tx;
-            tile[ty + 8 * k][tx] = (c < Cs && p < HW) ? __ldg(s + (long long)c * HW + p) : 0.f;
+            float v = (c < Cs && p < HW) ? __ldg(s + (long long)c * HW + p) : 0.f;
+            tile[ty + 8 * k][tx] = v > 0.f ? v : v * slope;
         }
         __syncthreads();
         // write: lanes along channels of one pixel
@@ -90,7 +93,9 @@ nchw_part_kernel(float* __restrict__ dst, const float* __restrict__ src, long lo
         for (int k = 0; k < 4; ++k) {
             const long long p = p0 + ty + 8 * k;
             const int c = c0 + tx;
-            tile[ty + 8 * k][tx] = (c < Cs && p < HW) ? __ldg(s + p * Cd + c) : 0.f;
+            float v = (c < Cs && p < HW) ? __ldg(s + p * Cd + c) : 0.f;
+            if (fwd && c < Cs && p < HW && !(__ldg(fwd + n * HW * Cd + c_off + p * Cd + c) > 0.f)) v *= slope;
+            tile[ty + 8 * k][tx] = v;
         }
         __syncthreads();
         float* d = dst + n_part * Cs * HW;
@@ -249,6 +254,28 @@ extern "C" int arf_nhwc_transpose(float* dst, const float* src, long long N, lon
     dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N);
     if (to_nchw) nchw_part_kernel<false><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dst, src, HW, C, C, 0, batch_shift);
     else nchw_part_kernel<true><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dst, src, HW, C, C, 0, batch_shift);
+    ARF_CHECK_LAUNCH();
+    return ARF_OK;
+}
+
+// NCHW part with a leaky ReLU fused into the copy (see nchw_part_kernel)
+extern "C" int arf_nhwc_pack_act(float* dst, const float* src, long long N, long long HW, int Cs, int Cd, int c_off,
+                                 float slope, void* stream) {
+    ARF_REQUIRE(dst && src);
+    if (N <= 0 || N > 65535 || HW <= 0 || Cs <= 0 || Cd <= 0 || c_off < 0 || c_off + Cs > Cd || (Cs + 31) / 32 > 65535) return ARF_EINVAL;
+    dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((Cs + 31) / 32), (unsigned)N);
+    nchw_part_kernel<true><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dst, src, HW, Cs, Cd, c_off, 0, slope, nullptr);
+    ARF_CHECK_LAUNCH();
+    return ARF_OK;
+}
+
+extern "C" int arf_nhwc_unpack_act(float* part, const float* packed_grad, const float* packed_fwd, long long N, long long HW,
+                                   int Cs, int Cd, int c_off, float slope, void* stream) {
+    ARF_REQUIRE(part && packed_grad && packed_fwd);
+    if (N <= 0 || N > 65535 || HW <= 0 || Cs <= 0 || Cd <= 0 || c_off < 0 || c_off + Cs > Cd || (Cs + 31) / 32 > 65535) return ARF_EINVAL;
+    dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((Cs + 31) / 32), (unsigned)N);
+    nchw_part_kernel<false><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(part, packed_grad, HW, Cs, Cd, c_off, 0, slope,
+                                                                            packed_fwd);
     ARF_CHECK_LAUNCH();
     return ARF_OK;
 }

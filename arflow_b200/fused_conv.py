@@ -189,25 +189,32 @@ def out_channel_pad(cout):
 
 class _NhwcConcat(torch.autograd.Function):
     """torch.cat(parts, dim=1) into a packed channels-last tensor with the channel count rounded up to `c_total`
-    (zero tail).  Parts may be NHWC or NCHW; each part's gradient comes back in the part's own layout."""
+    (zero tail).  Parts may be NHWC or NCHW; each part's gradient comes back in the part's own layout.  slopes[i] != 1
+    applies a leaky ReLU to part i on the way in (NCHW parts only) — the cost volume's activation, fused."""
 
     @staticmethod
-    def forward(ctx, c_total, *parts):
+    def forward(ctx, c_total, slopes, *parts):
         B, _, H, W = parts[0].shape
         dev, dt = parts[0].device, parts[0].dtype
         out = torch.empty((B, c_total, H, W), dtype=dt, device=dev, memory_format=CL)
         meta, off = [], 0
         with torch.cuda.device_of(out):
-            for p in parts:
+            for p, slope in zip(parts, slopes):
                 if p.shape[0] != B or p.shape[2:] != (H, W) or p.dtype != torch.float32 or not p.is_cuda:
                     raise ValueError("nhwc_concat: parts must be float32 CUDA tensors of equal batch and spatial size")
                 nhwc = is_nhwc(p)
                 if not nhwc:
                     p = p.contiguous()
                 C = p.shape[1]
-                _lib.call("arf_nhwc_pack", out.data_ptr(), p.data_ptr(), B, H * W, C, c_total, off, int(nhwc),
-                          _lib.stream_ptr())
-                meta.append((C, off, nhwc))
+                if slope != 1.0:
+                    if nhwc or C <= 4:
+                        raise NotImplementedError("nhwc_concat: fused activation needs an NCHW part with more than 4 channels")
+                    _lib.call("arf_nhwc_pack_act", out.data_ptr(), p.data_ptr(), B, H * W, C, c_total, off, float(slope),
+                              _lib.stream_ptr())
+                else:
+                    _lib.call("arf_nhwc_pack", out.data_ptr(), p.data_ptr(), B, H * W, C, c_total, off, int(nhwc),
+                              _lib.stream_ptr())
+                meta.append((C, off, nhwc, float(slope)))
                 off += C
             if off > c_total:
                 raise ValueError("nhwc_concat: parts exceed c_total")
@@ -216,31 +223,41 @@ class _NhwcConcat(torch.autograd.Function):
                           _lib.stream_ptr())
         ctx.meta = meta
         ctx.dims = (B, H, W, c_total)
+        if any(s != 1.0 for s in slopes):
+            ctx.save_for_backward(out)       # the activation mask is read back from the packed output
         return out
 
     @staticmethod
     def backward(ctx, gout):
         B, H, W, c_total = ctx.dims
         gout = gout.contiguous(memory_format=CL)
-        grads = [None]
+        fwd = ctx.saved_tensors[0] if ctx.saved_tensors else None
+        grads = [None, None]
         with torch.cuda.device_of(gout):
-            for i, (C, off, nhwc) in enumerate(ctx.meta):
-                if not ctx.needs_input_grad[i + 1]:
+            for i, (C, off, nhwc, slope) in enumerate(ctx.meta):
+                if not ctx.needs_input_grad[i + 2]:
                     grads.append(None)
                     continue
                 g = torch.empty((B, C, H, W), dtype=gout.dtype, device=gout.device,
                                 memory_format=CL if nhwc else torch.contiguous_format)
-                _lib.call("arf_nhwc_unpack", g.data_ptr(), gout.data_ptr(), B, H * W, C, c_total, off, int(nhwc),
-                          _lib.stream_ptr())
+                if slope != 1.0:
+                    _lib.call("arf_nhwc_unpack_act", g.data_ptr(), gout.data_ptr(), fwd.data_ptr(), B, H * W, C, c_total,
+                              off, slope, _lib.stream_ptr())
+                else:
+                    _lib.call("arf_nhwc_unpack", g.data_ptr(), gout.data_ptr(), B, H * W, C, c_total, off, int(nhwc),
+                              _lib.stream_ptr())
                 grads.append(g)
         return tuple(grads)
 
 
 def nhwc_concat(parts, multiple=8):
     """Channel concat of CUDA tensors into a packed channels-last tensor, channels padded up to `multiple`.
+    A part may be given as (tensor, negative_slope): leaky ReLU applied on the way in (NCHW parts).
     Returns (tensor, n_real_channels)."""
-    n = sum(p.shape[1] for p in parts)
-    return _NhwcConcat.apply(round_up(n, multiple), *parts), n
+    tensors = [p[0] if isinstance(p, tuple) else p for p in parts]
+    slopes = tuple(float(p[1]) if isinstance(p, tuple) else 1.0 for p in parts)
+    n = sum(t.shape[1] for t in tensors)
+    return _NhwcConcat.apply(round_up(n, multiple), slopes, *tensors), n
 
 
 class _DenseBlockNhwc(torch.autograd.Function):

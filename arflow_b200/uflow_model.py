@@ -309,7 +309,8 @@ class PWCFlow(nn.Module):
             f1n, w2n = normalize_features([f1, warped2], normalize=self._normalize_before_cost_volume,
                                           center=self._normalize_before_cost_volume, moments_across_channels=True,
                                           moments_across_images=True)
-            cost_volume = func.leaky_relu(ops.compute_cost_volume(f1n, w2n, max_displacement=4), negative_slope=alpha)
+            # the cost volume's leaky ReLU (uflow_model.py:185-186) rides on its NCHW -> NHWC pack
+            cost_volume = (ops.compute_cost_volume(f1n, w2n, max_displacement=4), alpha)
             if flow_up is None:
                 parts = [cost_volume, features1]
             elif context_up is None:

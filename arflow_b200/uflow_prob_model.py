@@ -146,8 +146,10 @@ class PWCProbFlow(nn.Module):
                 f1n, w2n = normalize_features([f1, warped2], normalize=self._normalize_before_cost_volume,
                                               center=self._normalize_before_cost_volume, moments_across_channels=True,
                                               moments_across_images=True)
-                cost_volumes.append(func.leaky_relu(ops.compute_cost_volume(f1n, w2n, max_displacement=4),
-                                                    negative_slope=self._leaky_relu_alpha))
+                cv = ops.compute_cost_volume(f1n, w2n, max_displacement=4)
+                # channels-last: the leaky ReLU rides on the NCHW -> NHWC pack of the concat (fused_conv.nhwc_concat)
+                cost_volumes.append((cv, self._leaky_relu_alpha) if nhwc else
+                                    func.leaky_relu(cv, negative_slope=self._leaky_relu_alpha))
             parts = [context_up, out_up] + cost_volumes + [features1]
             if nhwc:
                 context, out = decoder_level_nhwc(self._flow_layers[level], parts, self._leaky_relu_alpha)

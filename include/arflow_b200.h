@@ -214,6 +214,12 @@ int arf_pad_weight(float* dst, const float* src, int Co, int Ci, int KH, int KW,
                    int to_padded, void* stream);
 int arf_nhwc_unpack(float* part, const float* packed, long long N, long long HW, int Cs, int Cd, int c_off,
                     int part_nhwc, void* stream);
+/* pack / unpack of an NCHW part with a leaky ReLU fused into the copy (the cost volume's activation,
+ * models/uflow_model.py:185-186): dst slice = leaky(src);  part = packed_grad * (packed_fwd > 0 ? 1 : slope). */
+int arf_nhwc_pack_act(float* dst, const float* src, long long N, long long HW, int Cs, int Cd, int c_off, float slope,
+                      void* stream);
+int arf_nhwc_unpack_act(float* part, const float* packed_grad, const float* packed_fwd, long long N, long long HW, int Cs,
+                        int Cd, int c_off, float slope, void* stream);
 /* NCHW (N,C,HW) <-> channels-last (N,HW,C) copy through a tiled transpose, the NCHW side's batch index rotated by
  * batch_shift (the stacked flow directions read each other's features: `feature_pyramid2` of uflow_model.py:255-257):
  * to_nchw = 1: nchw[(n+shift) % N] = nhwc[n];  to_nchw = 0: nhwc[n] = nchw[(n+shift) % N]. */

@@ -180,3 +180,19 @@ def test_dense_block_manual_backward_matches_layerwise_autograd():
     assert torch.equal(out, y)
     for a, b in zip(got, ref):
         assert_close(a, b, 2e-5)
+
+
+def test_nhwc_concat_with_fused_leaky_relu():
+    """(tensor, slope) parts: leaky ReLU applied inside the pack, its gradient inside the unpack."""
+    from arflow_b200.fused_conv import CL, nhwc_concat
+    gen = torch.Generator().manual_seed(8)
+    a = torch.randn(2, 32, 13, 17, generator=gen).cuda().contiguous(memory_format=CL).requires_grad_(True)
+    cv = torch.randn(2, 81, 13, 17, generator=gen).cuda().requires_grad_(True)
+    out, n = nhwc_concat([a, (cv, 0.1)])
+    ref = torch.cat([a, func.leaky_relu(cv, negative_slope=0.1)], dim=1)
+    assert n == 113 and out.shape[1] == 120
+    assert torch.equal(out.detach()[:, :113], ref.detach())
+    w = torch.randn(out.shape, generator=gen).cuda()
+    g = torch.autograd.grad((out * w).sum(), [a, cv])
+    r = torch.autograd.grad((ref * w[:, :113]).sum(), [a, cv])
+    assert torch.equal(g[0], r[0]) and torch.equal(g[1], r[1])
