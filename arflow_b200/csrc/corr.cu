@@ -567,12 +567,14 @@ inline bool is_fast(const CorrGeom& g, bool bwd) {
 }  // namespace
 
 extern int g_warp_variant;   // warp.cu
+extern int g_trisolve_variant;   // stencil.cu
 
 extern "C" int arf_debug_set(int key, int value) {
     if (key == 0) { g_force_no_tma = value; return ARF_OK; }
     if (key == 1) { g_variant = value; return ARF_OK; }
     if (key == 2) { g_probe = value; return ARF_OK; }
     if (key == 3) { g_warp_variant = value; return ARF_OK; }
+    if (key == 4) { g_trisolve_variant = value; return ARF_OK; }
     return ARF_EINVAL;
 }
 

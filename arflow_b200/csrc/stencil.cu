@@ -12,6 +12,8 @@
 //        wavefront on the sub-rectangle below/right of the start pixel and reduces the squares.
 #include "common.cuh"
 
+int g_trisolve_variant = 0;   // test hook (arf_debug_set key 4): 1 = force the wavefront solve
+
 namespace {
 
 // ---------------------------------------------------------------------------- mat-vec -----
@@ -218,7 +220,8 @@ stencil_mv_bwd_kernel(const float* __restrict__ A, const float* __restrict__ X, 
 // Measured (B200, 64 systems of 112x256): 0.6 us per anti-diagonal.  The limiter is not DRAM latency but L1
 // wavefronts: thread <-> row makes every coefficient load touch 32 different sectors (5 arrays x 4 warps x 32
 // = 640 L1 wavefronts per step); a deeper register prefetch ring was tried and is slower (274 vs 219 us).
-// Next step (round 2): thread <-> column with a per-row affine scan, which makes all loads row-contiguous.
+// arf_trisolve therefore uses trisolve_scan_kernel below whenever a row fits one block; the wavefront stays
+// for the inverse-diagonal mode (sub-rectangles, no stores) and for rows wider than 1024.
 template <bool kUpper, bool kUnit>
 __device__ float wavefront(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ C,
                            const float* __restrict__ D, const float* __restrict__ X, float* __restrict__ Y, int M,
@@ -283,6 +286,179 @@ __device__ float wavefront(const float* __restrict__ A, const float* __restrict_
     return sumsq;
 }
 
+// ---------------------------------------------------------------------------- row scan ---
+// Same recurrence, thread <-> column, rows in sequence.  Inside one row everything above is known, so
+//   y_j = p_j + q_j y_(j-1),   p_j = (X - C up - D upleft) / A,   q_j = -B / A,
+// a first-order linear recurrence: affine maps compose associatively ((p,q) after (p',q') = (p + q p', q q')), so
+// a warp's 32 columns are an inclusive scan of 5 shuffle rounds, and the only thing a warp needs from its left
+// neighbour is one number per row, the y of the neighbour's last column (the carry).  Warps therefore run as a
+// pipeline, not in lock step: warp w publishes (row, carry) as one 8-byte shared store per row, warp w+1 polls
+// for the row tag.  Warp w runs about one hop ahead of warp w+1, a system costs M row-steps plus one hop per
+// warp (the wavefront: M + N - 1 steps), and there is no block barrier on the row-to-row dependent chain (the
+// first version had one per row plus a serial fold over the warp totals and ran 78 us against this one's time
+// in DESIGN.md section 3).  The carry is also the left neighbour's y across the warp seam, which the next row
+// needs as `upleft`.  Every load and store is row-contiguous (the wavefront's were 32 sectors per request).
+//
+// Coefficients come through a shared-memory ring filled by 4-byte cp.async (LDGSTS) kScanRing-1 rows ahead; each
+// thread reads back only what it copied itself, so cp.async.wait_group is the only synchronisation.  A register
+// ring does not work: loads retire through six counting scoreboards per warp, so waiting for the oldest row
+// also waits for the newest one, and the kernel ran at one DRAM latency per row (0.9 us) with one row or eight
+// rows of lookahead alike.  cp.async groups complete in order and are waited by count.  1/A and the products
+// with it are taken one row ahead, off the dependent chain.
+//
+// Carry slots are reused every kScanSlots rows; a __syncthreads at those rows keeps a fast producer from
+// overwriting a slot its consumer has not read (tags are row numbers, so a stale slot never matches).
+// Rounding: the scan reassociates the j-chain and multiplies by 1/A instead of dividing (fp32, fma); against
+// the f64 oracle the difference is a few ulp of the solution for the diagonally dominant systems this operator
+// is built for.  (q products overflow only where the sequential solve has already left fp32 range.)
+
+// 4-byte cp.async of `bytes` (4 or 0) source bytes, the rest zero-filled; src stays a mapped address either way
+__device__ __forceinline__ void cp4(uint32_t dst, const float* src, int bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+
+constexpr int kScanRing = 8;     // rows of coefficients in flight per block (power of two)
+constexpr int kScanSlots = 64;   // rows of carries between block barriers (power of two)
+
+static size_t scan_smem_bytes(int threads) {
+    return (size_t)kScanRing * 5 * threads * sizeof(float) + (size_t)kScanSlots * (threads / 32) * 8;
+}
+
+// Hides a loop invariant from the optimiser: left alone, nvcc rematerialises the per-thread bases, predicates and
+// strides of trisolve_scan_kernel inside the row loop (about 110 of its 200 instructions per row).
+template <class V> __device__ __forceinline__ V keep32(V v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
+template <class V> __device__ __forceinline__ V* keep64(V* p) {
+    asm volatile("" : "+l"(p));
+    return p;
+}
+
+template <bool kUpper>
+__global__ void __launch_bounds__(1024)
+trisolve_scan_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ C,
+                     const float* __restrict__ D, const float* __restrict__ X, float* __restrict__ Y, int M, int N) {
+    const size_t s = blockIdx.x;
+    const bool has_d = D != nullptr;
+    const int lj = threadIdx.x, lane = lj & 31, w = lj >> 5;
+    const int T = blockDim.x, nw = T >> 5;
+    const bool col = lj < N;
+
+    extern __shared__ __align__(16) unsigned char scan_smem[];
+    const uint32_t smem_u32 = (uint32_t)__cvta_generic_to_shared(scan_smem);
+    // ring: [kScanRing][T][5] floats (a, x, b, c, d); slots: [kScanSlots][nw] of (row << 32) | carry
+    const uint32_t slots_u32 = smem_u32 + kScanRing * 20 * T;
+    {
+        volatile unsigned long long* sl = reinterpret_cast<volatile unsigned long long*>(scan_smem + kScanRing * 20 * T);
+        for (int k = lj; k < kScanSlots * nw; k += T) sl[k] = ~0ull;
+    }
+
+    // A warp alone issues one instruction every few cycles, so the row time is the instruction count of the loop
+    // below (the first pipelined version spent 265 instructions per row, mostly 64-bit address arithmetic, and
+    // was no faster than the barrier version).  Addresses are therefore two 32-bit element offsets per thread
+    // (A/X/C rows are N wide, B/D rows N-1), stepped by one row per copy, on bases shifted so that C shares A's
+    // offset and D shares B's: lower solves read C and D one row up, (i-1, j) = offset - N, (i-1, j-1) = offset
+    // - (N-1); upper solves read them at the cell itself.  Threads outside the grid keep clamped, mapped offsets
+    // and copy zero bytes.
+    const int jc = col ? (kUpper ? N - 1 - lj : lj) : 0;                     // physical column, clamped
+    const bool hb = col && lj > 0 && N > 1;
+    const int jb = hb ? (kUpper ? jc : jc - 1) : 0;
+    const int stepA = keep32(kUpper ? -N : N), stepB = keep32(kUpper ? -(N - 1) : N - 1);
+    int oa = (kUpper ? (M - 1) * N : 0) + jc;                                // offsets of the next row to copy
+    int ob = (kUpper ? (M - 1) * (N - 1) : 0) + jb;
+    int oy = oa;                                                             // offset of the row being solved
+    const float* Ab = keep64(A + s * M * N);
+    const float* Xb = keep64(X + s * M * N);
+    const float* Bb = keep64(B + s * M * (N - 1));
+    const float* Cb = keep64(C + s * (M - 1) * N - (kUpper ? 0 : N));
+    const float* Db = keep64(has_d ? D + s * (M - 1) * (N - 1) - (kUpper ? 0 : N - 1) : Ab);
+    float* Yb = keep64(Y + s * M * N);
+    const int na = keep32(col ? 4 : 0), nb = keep32(hb ? 4 : 0), nd = keep32((hb && has_d) ? 4 : 0);
+    const uint32_t ring_me = keep32(smem_u32 + lj * 20), ring_stride = keep32((uint32_t)T * 20);
+    const uint32_t slot_me = keep32(slots_u32 + w * 8), slot_stride = keep32((uint32_t)nw * 8);
+    const bool publish = lane == 31 && w + 1 < nw;
+
+    auto issue = [&](int li, bool first) {
+        if (li < M) {
+            const uint32_t dst = ring_me + (li & (kScanRing - 1)) * ring_stride;
+            cp4(dst, Ab + oa, na);
+            cp4(dst + 4, Xb + oa, na);
+            cp4(dst + 8, Bb + ob, nb);
+            // row 0 has nothing above it; its shifted C / D addresses would lie before the arrays
+            cp4(dst + 12, first ? Ab : Cb + oa, first ? 0 : na);
+            cp4(dst + 16, first ? Ab : Db + ob, first ? 0 : nd);
+            oa += stepA;
+            ob += stepB;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // row li of the ring, scaled by 1/A: xi = X/A, q = -B/A, ci = C/A, di = D/A
+    struct Row { float xi, q, ci, di; };
+    auto scaled = [&](int li) {
+        const uint32_t src = ring_me + (li & (kScanRing - 1)) * ring_stride;
+        float a, x, b, c, d;
+        asm volatile("ld.shared.f32 %0, [%5];\n\tld.shared.f32 %1, [%5+4];\n\tld.shared.f32 %2, [%5+8];\n\t"
+                     "ld.shared.f32 %3, [%5+12];\n\tld.shared.f32 %4, [%5+16];"
+                     : "=f"(a), "=f"(x), "=f"(b), "=f"(c), "=f"(d)
+                     : "r"(src)
+                     : "memory");
+        a = na ? a : 1.f;
+        float inv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(a));
+        inv = fmaf(inv, fmaf(-a, inv, 1.f), inv);  // one Newton step: correctly rounded but for rare last-bit ties
+        return Row{x * inv, -b * inv, c * inv, d * inv};
+    };
+    auto peek = [&](uint32_t addr) {
+        unsigned long long v;
+        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+        return v;
+    };
+
+    issue(0, true);
+#pragma unroll
+    for (int r = 1; r < kScanRing - 1; ++r) issue(r, false);
+    asm volatile("cp.async.wait_group %0;" ::"n"(kScanRing - 2) : "memory");   // row 0 has landed
+    Row nxt = scaled(0);
+    __syncthreads();                               // slot tags initialised
+    float up = 0.f, upleft = 0.f;
+    for (int li = 0; li < M; ++li) {
+        const Row k = nxt;
+        float p = fmaf(-k.ci, up, fmaf(-k.di, upleft, k.xi));
+        float q = k.q;
+        const uint32_t in = slot_me + (li & (kScanSlots - 1)) * slot_stride;
+        unsigned long long cv = w > 0 ? peek(in) : 0ull;   // first look at the carry, overlapped with the scan
+        issue(li + kScanRing - 1, false);          // into the slot row li-1 was read from
+        asm volatile("cp.async.wait_group %0;" ::"n"(kScanRing - 2) : "memory");   // row li+1 has landed
+        nxt = scaled(li + 1);                      // independent of this row's chain (past M: an unused old slot)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float pp = __shfl_up_sync(0xffffffffu, p, o), qq = __shfl_up_sync(0xffffffffu, q, o);
+            if (lane >= o) {
+                p = fmaf(q, pp, p);
+                q *= qq;
+            }
+        }
+        // the left neighbour's map, so that its y needs no further shuffle once the carry is known
+        const float pl = __shfl_up_sync(0xffffffffu, p, 1), ql = __shfl_up_sync(0xffffffffu, q, 1);
+        float carry = 0.f;                         // y of the last column of the warp to the left
+        if (w > 0) {
+            while ((unsigned)(cv >> 32) != (unsigned)li) cv = peek(in);
+            carry = __uint_as_float((unsigned)cv);
+        }
+        const float y = fmaf(q, carry, p);
+        if (publish) {
+            const unsigned long long v = ((unsigned long long)(unsigned)li << 32) | __float_as_uint(y);
+            asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(in + 8), "l"(v) : "memory");
+        }
+        if (na) Yb[oy] = y;
+        oy += stepA;
+        upleft = lane == 0 ? carry : fmaf(ql, carry, pl);
+        up = y;
+        if ((li & (kScanSlots - 1)) == kScanSlots - 1) __syncthreads();
+    }
+}
+
 template <bool kUpper>
 __global__ void trisolve_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ C,
                                 const float* __restrict__ D, const float* __restrict__ X, float* __restrict__ Y, int M,
@@ -340,11 +516,24 @@ extern "C" int arf_stencil_mv_bwd(const float* A, const float* X, const float* g
 
 extern "C" int arf_trisolve(const float* A, const float* B, const float* C, const float* D, const float* X, float* Y,
                             long long systems, int M, int N, int upper, void* stream) {
-    ARF_REQUIRE(A && B && C && X && Y && systems > 0 && systems <= 0x7fffffffLL && M > 0 && N > 0);
-    if (M > 1024) return ARF_EUNSUPPORTED;     // thread <-> row
+    ARF_REQUIRE(A && (B || N == 1) && (C || M == 1) && X && Y && systems > 0 && systems <= 0x7fffffffLL && M > 0 &&
+                N > 0);   // B / C are empty (NULL allowed) for single-column / single-row systems
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 1024 && (long long)M * N < 0x7fffffffLL && g_trisolve_variant != 1) {  // thread <-> column, row scan
+        const int threads = (N + 31) / 32 * 32;
+        const size_t smem = scan_smem_bytes(threads);   // 44 KB at N = 256, 176 KB at 1024
+        auto kern = upper ? trisolve_scan_kernel<true> : trisolve_scan_kernel<false>;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+        kern<<<(int)systems, threads, smem, st>>>(A, B, C, D, X, Y, M, N);
+        ARF_CHECK_LAUNCH();
+        return ARF_OK;
+    }
+    if (M > 1024) return ARF_EUNSUPPORTED;       // thread <-> row wavefront
     const int threads = (M + 31) / 32 * 32;
     const size_t smem = 2 * (threads + 1) * sizeof(float);
-    cudaStream_t st = (cudaStream_t)stream;
     if (upper) trisolve_kernel<true><<<(int)systems, threads, smem, st>>>(A, B, C, D, X, Y, M, N);
     else trisolve_kernel<false><<<(int)systems, threads, smem, st>>>(A, B, C, D, X, Y, M, N);
     ARF_CHECK_LAUNCH();

@@ -58,7 +58,8 @@ int         arf_version(void);
 const char* arf_error_string(int code);
 /* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
 long long   arf_launch_count(void);
-/* Test hook. key 0: value != 0 forces the non-TMA (cp.async) staging path of the tiled kernels. */
+/* Test hook. key 0: value != 0 forces the non-TMA (cp.async) staging path of the tiled kernels; keys 1-2 pick
+ * correlation variants, key 3 warp variants (1 direct, 2 window), key 4 value 1 forces the wavefront solve. */
 int         arf_debug_set(int key, int value);
 
 /* ---------------------------------------------------------------- correlation ---------- */
@@ -244,7 +245,8 @@ int arf_stencil_mv_bwd(const float* A, const float* X, const float* gY, float* d
 /* forward_substitution (upper=0) / backward_substitution (upper=1) of triag_solve_cuda
  * (utils/triag_solve/triag_solve.cpp:12-36, triag_solve_cuda.cu:7-69; Python twins triag_solve.py:76-115).
  * A: (S,M,N) diagonal, B: (S,M,N-1) left/right, C: (S,M-1,N) above/below, D: (S,M-1,N-1) diagonal neighbour
- * (may be NULL), X -> Y: (S,M,N); S = batch*channels systems.  Y may not alias X. M <= 1024. */
+ * (may be NULL), X -> Y: (S,M,N); S = batch*channels systems.  Y may not alias X.  N <= 1024 runs the row-scan
+ * kernel, wider systems the anti-diagonal wavefront (M <= 1024, else ARF_EUNSUPPORTED). */
 int arf_trisolve(const float* A, const float* B, const float* C, const float* D, const float* X, float* Y,
                  long long systems, int M, int N, int upper, void* stream);
 

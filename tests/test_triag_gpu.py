@@ -85,3 +85,41 @@ def test_solve_inverts_product_at_config3_size():
     taps[:, 4:6, :-1, :] = C
     taps[:, 6:8, :-1, :-1] = D
     assert_close(ts.matrix_vector_product_general(taps, X, k=1), ts.matrix_vector_product(A, B, C, D, X), RTOL_VALUE)
+
+
+@pytest.mark.parametrize("M,N", [(1, 1), (1, 40), (9, 1), (5, 31), (7, 33), (20, 300), (3, 1024), (12, 1030)])
+@pytest.mark.parametrize("with_d", [True, False])
+def test_row_scan_and_wavefront_solves_agree_with_oracle(oracle, M, N, with_d):
+    """arf_trisolve picks the row-scan kernel for N <= 1024 and the anti-diagonal wavefront above that
+    (arf_debug_set key 4 = 1 forces the wavefront).  Both follow triag_solve.py:76-115; ragged widths
+    cover the warp seams, single rows / columns the degenerate recurrences."""
+    from arflow_b200 import _lib, triag_solve as ts
+    gen = torch.Generator().manual_seed(M * 1000 + N)
+    K, L = 2, 2
+    A = 1.0 + torch.rand(K, L, M, N, generator=gen)
+    B = 0.4 * torch.randn(K, L, M, max(N - 1, 0), generator=gen)
+    C = 0.4 * torch.randn(K, L, max(M - 1, 0), N, generator=gen)
+    D = 0.2 * torch.randn(K, L, max(M - 1, 0), max(N - 1, 0), generator=gen) if with_d else None
+    X = torch.randn(K, L, M, N, generator=gen)
+    a, b, c, x = (t.cuda() for t in (A, B, C, X))
+    d = D.cuda() if with_d else None
+
+    def solve(upper):
+        if with_d:
+            return (ts.backward_substitution if upper else ts.forward_substitution)(a, b, c, d, x)
+        y = torch.empty_like(x)                      # the C-ABI takes D = NULL (three-array systems)
+        _lib.call("arf_trisolve", a.data_ptr(), b.data_ptr(), c.data_ptr(), None, x.data_ptr(), y.data_ptr(),
+                  K * L, M, N, int(upper), _lib.stream_ptr())
+        return y
+
+    for upper in (False, True):
+        ref = oracle.substitution(A, B, C, D, X, upper=upper)
+        outs = []
+        for variant in (0, 1):
+            _lib.load().arf_debug_set(4, variant)
+            try:
+                outs.append(solve(upper))
+            finally:
+                _lib.load().arf_debug_set(4, 0)
+            assert_close(outs[-1], ref, RTOL_VALUE, "upper=%s variant=%d" % (upper, variant))
+        assert_close(outs[0], outs[1], RTOL_VALUE, "scan vs wavefront")

@@ -194,6 +194,9 @@ def main():
                 return lambda: lib.arf_trisolve(A.data_ptr(), Bc.data_ptr(), Cc.data_ptr(), Dc.data_ptr(), X.data_ptr(),
                                                 Y.data_ptr(), N * 2, H, W, 0, cs())
             report("trisolve", (N, 2, H, W), N * 2 * H * W * 24, N * 2 * H * W * 8, *time_graph(mkt, N * 2 * H * W * 24))
+            lib.arf_debug_set(4, 1)
+            report("trisolve_wavefront", (N, 2, H, W), N * 2 * H * W * 24, N * 2 * H * W * 8, *time_graph(mkt, N * 2 * H * W * 24))
+            lib.arf_debug_set(4, 0)
     if args.what in ("glue", "all"):
         # the streaming kernels around the cuDNN convolutions (fused_conv.py): L1-level shapes of the chairs_uflow step
         nrows, C = 16 * 96 * 128, 128

@@ -25,6 +25,7 @@ prof census_fwd census_fwd_kernel census --shapes 8x3x384x512
 prof census_bwd census_bwd_kernel census --shapes 8x3x384x512
 prof stencil_fwd 'stencil_mv_kernel' stencil
 prof stencil_bwd 'stencil_mv_bwd_kernel' stencil
+prof trisolve trisolve_scan_kernel stencil
 prof epilogue_fwd bias_leaky_nhwc_fwd_kernel glue
 prof epilogue_bwd bias_leaky_nhwc_bwd_kernel glue
 prof nhwc_pack nhwc_part_kernel glue
