@@ -87,12 +87,13 @@ def test_solve_inverts_product_at_config3_size():
     assert_close(ts.matrix_vector_product_general(taps, X, k=1), ts.matrix_vector_product(A, B, C, D, X), RTOL_VALUE)
 
 
-@pytest.mark.parametrize("M,N", [(1, 1), (1, 40), (9, 1), (5, 31), (7, 33), (20, 300), (3, 1024), (12, 1030)])
+@pytest.mark.parametrize("M,N", [(1, 1), (1, 40), (9, 1), (5, 31), (7, 33), (20, 300), (3, 1024), (70, 1000), (12, 1030)])
 @pytest.mark.parametrize("with_d", [True, False])
 def test_row_scan_and_wavefront_solves_agree_with_oracle(oracle, M, N, with_d):
     """arf_trisolve picks the row-scan kernel for N <= 1024 and the anti-diagonal wavefront above that
     (arf_debug_set key 4 = 1 forces the wavefront).  Both follow triag_solve.py:76-115; ragged widths
-    cover the warp seams, single rows / columns the degenerate recurrences."""
+    cover the warp seams, single rows / columns the degenerate recurrences, 70 x 1000 the reuse of the carry slots
+    (every 64 rows) with 32 warps in the pipeline."""
     from arflow_b200 import _lib, triag_solve as ts
     gen = torch.Generator().manual_seed(M * 1000 + N)
     K, L = 2, 2
