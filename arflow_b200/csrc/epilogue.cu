@@ -94,7 +94,16 @@ __global__ void bias_grad_finalize_kernel(const float* __restrict__ partials, fl
 inline int nchunks_of(long long HW) { return (int)((HW + kEChunk - 1) / kEChunk); }
 
 // ---- NHWC (channels-last) variants: y is a (rows = N*H*W) x C row-major matrix --------------------------------
-constexpr int kERows = 256;       // rows of the matrix handled by one CTA of the backward
+constexpr int kERows = 256;       // most rows of the matrix one CTA of the backward handles
+
+// Rows per CTA of the backward: 256 when that still gives every SM four CTAs, else halved down to 32.  The coarse
+// pyramid levels (49152, 12288, 3072 rows) ran on 192, 48 and 12 CTAs with the fixed 256 and were latency-bound
+// (22, 13 and 9 us per launch in the step's launch list).
+static int nhwc_rows_per_cta(long long rows) {
+    int r = kERows;
+    while (r > 32 && rows / r < 4LL * ARF_NUM_SMS) r >>= 1;
+    return r;
+}
 
 __global__ void __launch_bounds__(kEThreads)
 bias_leaky_nhwc_fwd_kernel(const float* src, float* dst, long long dst_ld, const float* __restrict__ bias, long long total,
@@ -124,15 +133,16 @@ bias_leaky_nhwc_fwd_kernel(const float* src, float* dst, long long dst_ld, const
     }
 }
 
-// One CTA: kERows rows x all C columns.  Thread t owns column group (t % G) (4 columns when vec, else 1) and walks
+// One CTA: rpc rows x all C columns.  Thread t owns column group (t % G) (4 columns when vec, else 1) and walks
 // rows t / G, t / G + 256 / G, ...; the per-thread column sums are reduced through shared memory, one partial row
 // of C sums per CTA.
 __global__ void __launch_bounds__(kEThreads)
 bias_leaky_nhwc_bwd_kernel(const float* __restrict__ gy, long long gy_ld, const float* __restrict__ y, long long y_ld,
-                           float* __restrict__ g, float* __restrict__ partials, long long rows, int C, float slope, int vec) {
+                           float* __restrict__ g, float* __restrict__ partials, long long rows, int C, float slope, int vec,
+                           int rpc) {
     extern __shared__ float sacc[];          // kEThreads * 4 floats
-    const long long r0 = (long long)blockIdx.x * kERows;
-    const long long r1 = r0 + kERows < rows ? r0 + kERows : rows;
+    const long long r0 = (long long)blockIdx.x * rpc;
+    const long long r1 = r0 + rpc < rows ? r0 + rpc : rows;
     const int w = vec ? 4 : 1;
     const int G = C / w;                     // column groups per row
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -211,7 +221,8 @@ bias_grad_nhwc_finalize_kernel(const float* __restrict__ partials, float* __rest
 
 extern "C" long long arf_bias_leaky_nhwc_num_partials(long long rows, int C) {
     if (rows <= 0 || C <= 0) return ARF_EINVAL;
-    return ((rows + kERows - 1) / kERows) * C;
+    const int rpc = nhwc_rows_per_cta(rows);
+    return ((rows + rpc - 1) / rpc) * C;
 }
 
 extern "C" int arf_bias_leaky_nhwc_fwd(float* y, const float* bias, long long rows, int C, float slope, void* stream) {
@@ -241,13 +252,14 @@ extern "C" int arf_bias_leaky_nhwc_bwd_ld(const float* gy, long long gy_ld, cons
     ARF_REQUIRE(gy && y && g);
     ARF_REQUIRE(rows > 0 && C > 0 && gy_ld >= C && y_ld >= C);
     if (dbias) ARF_REQUIRE(partials != nullptr);
-    const long long nblk = (rows + kERows - 1) / kERows;
+    const int rpc = nhwc_rows_per_cta(rows);
+    const long long nblk = (rows + rpc - 1) / rpc;
     if (nblk > 0x7fffffffLL) return ARF_EINVAL;
     const int vec = ((uintptr_t)gy % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)g % 16 == 0) && (C % 4 == 0) &&
                     (gy_ld % 4 == 0) && (y_ld % 4 == 0);
     cudaStream_t st = (cudaStream_t)stream;
     bias_leaky_nhwc_bwd_kernel<<<(unsigned)nblk, kEThreads, kEThreads * 4 * sizeof(float), st>>>(
-        gy, gy_ld, y, y_ld, g, dbias ? partials : nullptr, rows, C, slope, vec);
+        gy, gy_ld, y, y_ld, g, dbias ? partials : nullptr, rows, C, slope, vec, rpc);
     ARF_CHECK_LAUNCH();
     if (dbias) {
         bias_grad_nhwc_finalize_kernel<<<arf_cdiv(C, 32), dim3(32, 32), 0, st>>>(partials, dbias, nblk, C);
