@@ -40,12 +40,14 @@ class UFlowLoss(nn.modules.Module):
         :param target: image pairs B x 6 x H x W
         :return: total_loss, loss_warp, loss_smooth, mean |flow| at level 0, forward mask
         """
-        flow12_0 = output[0][:, 0:2]
-        flow21_0 = output[0][:, 2:4]
-        flow12_2 = output[2][:, 0:2]
-        flow21_2 = output[2][:, 2:4]
-        im1_0 = target[:, :3]
-        im2_0 = target[:, 3:]
+        # every slice below is read by two or three kernels that need dense NCHW: one copy each here instead of one per
+        # consumer (six image and four full-resolution flow copies per step in the launch list otherwise)
+        flow12_0 = output[0][:, 0:2].contiguous()
+        flow21_0 = output[0][:, 2:4].contiguous()
+        flow12_2 = output[2][:, 0:2].contiguous()
+        flow21_2 = output[2][:, 2:4].contiguous()
+        im1_0 = target[:, :3].contiguous()
+        im2_0 = target[:, 3:].contiguous()
 
         l1, mask1 = self._direction(im1_0, im2_0, flow12_0, flow21_2)
         loss_warp = self.cfg.w_census * l1

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as func
 
-from .fused_conv import (CL, _zeros_cl, conv_bias_leaky, conv_plain, dense_block_nhwc, nhwc_concat, out_channel_pad,
+from .fused_conv import (CL, _zeros_cl, conv_transpose_bias, conv_bias_leaky, conv_plain, dense_block_nhwc, nhwc_concat, out_channel_pad,
                          pad_in_channels, pad_weight, to_nchw)
 
 
@@ -157,8 +157,7 @@ def refine_nhwc(refine_model, context, out, alpha):
 
 def context_up_nhwc(up, context):
     """ConvTranspose2d x2 of the context features, channels-last in and out."""
-    return func.conv_transpose2d(context, up.weight.contiguous(memory_format=CL), up.bias, up.stride, up.padding,
-                                 up.output_padding, up.groups, up.dilation)
+    return conv_transpose_bias(up, context)
 
 
 class PWCFeaturePyramid(nn.Module):

@@ -196,3 +196,26 @@ def test_nhwc_concat_with_fused_leaky_relu():
     g = torch.autograd.grad((out * w).sum(), [a, cv])
     r = torch.autograd.grad((ref * w[:, :113]).sum(), [a, cv])
     assert torch.equal(g[0], r[0]) and torch.equal(g[1], r[1])
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 12, 16), (1, 32, 5, 7)])
+def test_conv_transpose_bias_matches_torch(shape):
+    """context up-sampling (models/uflow_model.py:283-291): ConvTranspose2d(32, 32, 4, 2, 1) on a channels-last input
+    with the bias added by the fused pass; values and the three gradients against nn.ConvTranspose2d itself."""
+    from arflow_b200.fused_conv import CL, conv_transpose_bias
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(5)
+        up = nn.ConvTranspose2d(32, 32, 4, 2, 1).cuda()
+        x = torch.randn(shape, device="cuda").contiguous(memory_format=CL).requires_grad_(True)
+        ref = up(x)
+        w = torch.randn_like(ref)
+        rg = torch.autograd.grad((ref * w).sum(), [x, up.weight, up.bias])
+        out = conv_transpose_bias(up, x)
+        og = torch.autograd.grad((out * w).sum(), [x, up.weight, up.bias])
+        assert_close(out, ref, 1e-5, "conv_transpose + bias")
+        for a, b, name in zip(og, rg, ("dx", "dw", "db")):
+            assert_close(a, b, 1e-4, name)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
