@@ -7,7 +7,7 @@ Data-parallel modes (world_size > 1):
     all-reduce of the whole flat buffer is ONE eager NCCL call between two graphs, Adam is the second graph.
     (Capturing the NCCL calls themselves inside the step graph hung on this pool's B200 boxes — torch 2.11 /
     NCCL 2.28.9, with and without the watchdog's async error handling — so the collective stays outside;
-    22.9 MB over NVLink is ~0.1 ms against a ~29 ms step.)
+    22.9 MB over NVLink is ~0.1 ms against a ~14.5 ms step.)
 
 
 Replaces, for the benchmark driver only, the per-step body of trainer/uflow_trainer.py:30-73 of the
@@ -18,7 +18,7 @@ config's lr/betas/eps), restructured for the B200:
     with the rest of backward),
   * no host synchronisation inside the step (the reference reads four `.item()`s and one level-
     dropout draw per level from the host), so the whole step is captured once in a CUDA graph and
-    replayed: launch latency of the ~700 small kernels disappears.
+    replayed: launch latency of the ~660 kernels of a step disappears.
 """
 import torch
 import torch.distributed as dist
