@@ -219,3 +219,30 @@ def test_conv_transpose_bias_matches_torch(shape):
             assert_close(a, b, 1e-4, name)
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("shape,bias", [((2, 32, 12, 16), True), ((1, 64, 7, 9), True), ((2, 32, 5, 40), False),
+                                        ((3, 32, 33, 70), True)])
+def test_flow_head_conv_gradients_match_torch(shape, bias):
+    """Conv2d(Cin, 2, 3, padding=1) on a channels-last input (models/uflow_model.py:139-143): output, input gradient
+    (cuDNN) and the weight / bias gradients of arf_conv3x3_small_wgrad against torch's own fp32 convolution; widths
+    that are not multiples of 4 or of the 32-pixel run, one and two channel groups."""
+    from arflow_b200.fused_conv import CL, _FlowOutConv, conv_plain
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(shape[1] + shape[3])
+        conv = nn.Conv2d(shape[1], 2, 3, padding=1, bias=bias).cuda()
+        x = torch.randn(shape, device="cuda").contiguous(memory_format=CL).requires_grad_(True)
+        params = [x, conv.weight] + ([conv.bias] if bias else [])
+        ref = conv(x)
+        w = torch.randn_like(ref)
+        rg = torch.autograd.grad((ref * w).sum(), params)
+        out = conv_plain(conv, x)
+        assert out.is_contiguous() and isinstance(out.grad_fn, _FlowOutConv._backward_cls)
+        og = torch.autograd.grad((out * w).sum(), params)
+        assert_close(out, ref, 1e-5, "flow head")
+        for a, b, name in zip(og, rg, ("dx", "dw", "db")):
+            assert_close(a, b, 1e-4, name)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
