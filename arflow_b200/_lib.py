@@ -48,8 +48,9 @@ PROTOTYPES = {
     "arf_bias_leaky_nhwc_num_partials": [ctypes.c_longlong, c_int],
     "arf_bias_leaky_nhwc_fwd": [_P, _P, ctypes.c_longlong, c_int, c_float, _P],
     "arf_bias_leaky_nhwc_bwd": [_P, _P, _P, _P, _P, ctypes.c_longlong, c_int, c_float, _P],
-    "arf_conv3x3_small_wgrad_workspace": [c_int, c_int, c_int, c_int, c_int],
-    "arf_conv3x3_small_wgrad": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
+    "arf_conv3x3_small_fwd": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
+    "arf_conv3x3_small_bwd_workspace": [c_int, c_int, c_int, c_int, c_int],
+    "arf_conv3x3_small_bwd": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
     "arf_bias_leaky_nhwc_bwd_ld": [_P, ctypes.c_longlong, _P, ctypes.c_longlong, _P, _P, _P, ctypes.c_longlong, c_int, c_float, _P],
     "arf_bias_leaky_nhwc_fwd_ld": [_P, _P, ctypes.c_longlong, _P, ctypes.c_longlong, c_int, c_float, _P],
     "arf_nhwc_unpack_add": [_P, _P, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, c_int, _P],
@@ -70,7 +71,7 @@ PROTOTYPES = {
 }
 _RESTYPES = {"arf_error_string": ctypes.c_char_p, "arf_launch_count": ctypes.c_longlong,
              "arf_featnorm_workspace": ctypes.c_longlong, "arf_bias_leaky_num_partials": ctypes.c_longlong, "arf_bias_leaky_nhwc_num_partials": ctypes.c_longlong,
-             "arf_conv3x3_small_wgrad_workspace": ctypes.c_longlong}
+             "arf_conv3x3_small_bwd_workspace": ctypes.c_longlong}
 
 _lib = None
 

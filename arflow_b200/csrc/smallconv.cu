@@ -1,15 +1,20 @@
-// Weight and bias gradient of the flow-output convolutions of the PWC decoders (sm_100a).
+// The flow-output convolutions of the PWC decoders, forward and backward (sm_100a).
 //
 // Every pyramid level ends in Conv2d(32, 2, 3, padding=1) on the dense block's context features, and the refinement
-// network ends in the same shape (models/uflow_model.py:139-143, 232-249).  As an implicit GEMM that weight gradient
-// is 2 x 288 outputs over K = N*H*W pixels: cuDNN runs `wgrad_alg0_engine_NHWC` for it, 145 us at 16 x 96 x 128 (plus
-// 12 us for ATen's bias reduction), although the operand is 25 MB (4 us of HBM time) and the arithmetic is 0.2 GFLOP.
-// This kernel streams the channels-last input once in fp32 (no TF32 rounding):
+// network ends in the same shape (models/uflow_model.py:139-143, 232-249).  As implicit GEMMs these are 2-wide: cuDNN
+// pads the channels and runs 256-wide tiles - at 16 x 96 x 128 the forward costs 67 us (two padding kernels, fprop,
+// ATen bias add, NHWC -> NCHW copy), the input gradient 33 us and `wgrad_alg0_engine_NHWC` 145 us (plus 12 us for
+// ATen's bias reduction), although the operand is 25 MB (4 us of HBM time) and the arithmetic is 0.2 GFLOP per pass.
+// These kernels stream the channels-last operand once, in fp32 (no TF32 rounding):
+//   y[n][co][y][x]     = b[co] + sum_{kh,kw,ci} w[co][kh][kw][ci] * X[n][y+kh-1][x+kw-1][ci]          (NCHW out)
+//   dX[n][y][x][ci]    = sum_{co,kh,kw} gy[n][co][y-kh+1][x-kw+1] * w[co][kh][kw][ci]
 //   dW[co][kh][kw][ci] = sum_{n,y,x} gy[n][co][y][x] * X[n][y+kh-1][x+kw-1][ci]
 //   db[co]             = sum_{n,y,x} gy[n][co][y][x]
-// lane <-> input channel (32 per channel group), a warp walks a 32-pixel run of one image row with the 3 x 3 x Cout
-// neighbourhood of gy in registers (sliding window, 3 * Cout broadcast loads per pixel), loads of four pixels issued
-// before their use.  Per-CTA partial sums, then a fixed-order finalize: deterministic.
+// lane <-> input channel (32 per channel group), a warp walks a 32-pixel run of one image row.  Backward: the 3 x 3
+// x Cout neighbourhood of gy slides along in registers (3 * Cout broadcast loads per pixel) and feeds both gradients;
+// per-CTA partial sums of dW / db, then a fixed-order finalize (deterministic).  Forward: the 3 x 3 neighbourhood of
+// X slides along, per-lane partial dot products of a run go through shared memory so that the sum over the 32
+// channels and the NCHW store are done with lane <-> pixel.  Loads of four pixels are issued before their use.
 #include "common.cuh"
 
 namespace {
@@ -17,10 +22,11 @@ namespace {
 constexpr int kSWarps = 8;      // warps (pixel runs) per CTA
 constexpr int kSRun = 32;       // pixels per run
 
-template <int kCout>
+template <int kCout, bool kDgrad>
 __global__ void __launch_bounds__(kSWarps * 32)
-conv3x3_small_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ partials, int N,
-                           int H, int W, int Cin, int runs_per_row) {
+conv3x3_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ wt,
+                         float* __restrict__ gx, float* __restrict__ partials, int N, int H, int W, int Cin,
+                         int runs_per_row) {
     __shared__ float red[kSWarps][kCout * 9 + kCout][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int cg = blockIdx.y;                                   // channel group of 32
@@ -34,12 +40,21 @@ conv3x3_small_wgrad_kernel(const float* __restrict__ x, const float* __restrict_
 #pragma unroll
         for (int t = 0; t < 9; ++t) acc[co][t] = 0.f;
     }
+    float wr[kCout][9];                                          // w[co][tap][this lane's channel]
+    if (kDgrad) {
+#pragma unroll
+        for (int co = 0; co < kCout; ++co)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) wr[co][t] = __ldg(wt + ((long long)co * 9 + t) * Cin + cg * 32 + lane);
+    }
     if (run < nrun) {
         const int rx = (int)(run % runs_per_row);
         const long long t = run / runs_per_row;
         const int yy = (int)(t % H), n = (int)(t / H);
         const int x0 = rx * kSRun, x1 = x0 + kSRun < W ? x0 + kSRun : W;
-        const float* xr = x + ((long long)n * H + yy) * W * Cin + cg * 32 + lane;
+        const long long row_off = ((long long)n * H + yy) * W * Cin + cg * 32 + lane;
+        const float* xr = x + row_off;
+        float* gxr = kDgrad ? gx + row_off : nullptr;
         const float* gyn = gy + (long long)n * kCout * H * W;
         // gy[n][co][yy + 1 - kh][cx], zero outside the image (the convolution's zero padding seen from the input side)
         auto ld = [&](int co, int kh, int cx) {
@@ -69,13 +84,17 @@ conv3x3_small_wgrad_kernel(const float* __restrict__ x, const float* __restrict_
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
+                float dxv = 0.f;
 #pragma unroll
                 for (int co = 0; co < kCout; ++co) {
 #pragma unroll
                     for (int kh = 0; kh < 3; ++kh) {
                         win[co][kh][2] = gn[i][co][kh];
 #pragma unroll
-                        for (int kw = 0; kw < 3; ++kw) acc[co][kh * 3 + kw] = fmaf(xv[i], win[co][kh][2 - kw], acc[co][kh * 3 + kw]);
+                        for (int kw = 0; kw < 3; ++kw) {
+                            acc[co][kh * 3 + kw] = fmaf(xv[i], win[co][kh][2 - kw], acc[co][kh * 3 + kw]);
+                            if (kDgrad) dxv = fmaf(win[co][kh][2 - kw], wr[co][kh * 3 + kw], dxv);
+                        }
                     }
                     if (xx + i < x1) sb[co] += win[co][1][1];               // gy at the pixel itself
 #pragma unroll
@@ -84,6 +103,7 @@ conv3x3_small_wgrad_kernel(const float* __restrict__ x, const float* __restrict_
                         win[co][kh][1] = win[co][kh][2];
                     }
                 }
+                if (kDgrad && xx + i < x1) gxr[(long long)(xx + i) * Cin] = dxv;
             }
         }
     }
@@ -112,6 +132,88 @@ conv3x3_small_wgrad_kernel(const float* __restrict__ x, const float* __restrict_
     }
 }
 
+constexpr int kFWarps = 4;      // forward: warps per CTA (each owns kCout x 32 x 33 floats of shared memory)
+
+template <int kCout>
+__global__ void __launch_bounds__(kFWarps * 32)
+conv3x3_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ bias,
+                         float* __restrict__ y, int N, int H, int W, int Cin, int runs_per_row) {
+    __shared__ float part[kFWarps][kCout][kSRun][33];            // [pixel of the run][channel lane], padded
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long run = (long long)blockIdx.x * kFWarps + w;
+    const long long nrun = (long long)N * H * runs_per_row;
+    if (run >= nrun) return;                                     // no block-wide barrier below
+    const int rx = (int)(run % runs_per_row);
+    const long long t = run / runs_per_row;
+    const int yy = (int)(t % H), n = (int)(t / H);
+    const int x0 = rx * kSRun, x1 = x0 + kSRun < W ? x0 + kSRun : W;
+    float acc[kCout][kSRun / 32];                                // this lane's output pixel (lane <-> pixel at the end)
+#pragma unroll
+    for (int co = 0; co < kCout; ++co) acc[co][0] = 0.f;
+    for (int cg = 0; cg < Cin / 32; ++cg) {
+        float wr[kCout][9];
+#pragma unroll
+        for (int co = 0; co < kCout; ++co)
+#pragma unroll
+            for (int tp = 0; tp < 9; ++tp) wr[co][tp] = __ldg(wt + ((long long)co * 9 + tp) * Cin + cg * 32 + lane);
+        const float* xn = x + (long long)n * H * W * Cin + cg * 32 + lane;
+        // X[n][yy - 1 + r][cx][lane's channel], zero outside the image
+        auto ld = [&](int r, int cx) {
+            const int ry = yy - 1 + r;
+            const bool ok = ry >= 0 && ry < H && cx >= 0 && cx < W;
+            return ok ? __ldg(xn + ((long long)ry * W + cx) * Cin) : 0.f;
+        };
+        float win[3][3];                                         // [kh][kw]: column xx - 1 + kw
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            win[r][0] = ld(r, x0 - 1);
+            win[r][1] = ld(r, x0);
+        }
+        for (int xx = x0; xx < x1; xx += 4) {
+            float xn4[4][3];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) xn4[i][r] = ld(r, xx + i + 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) win[r][2] = xn4[i][r];
+#pragma unroll
+                for (int co = 0; co < kCout; ++co) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) s = fmaf(win[r][kw], wr[co][r * 3 + kw], s);
+                    if (xx + i < x1) part[w][co][xx + i - x0][lane] = s;
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    win[r][0] = win[r][1];
+                    win[r][1] = win[r][2];
+                }
+            }
+        }
+        __syncwarp();
+        if (x0 + lane < x1) {
+#pragma unroll
+            for (int co = 0; co < kCout; ++co) {
+                float s = 0.f;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) s += part[w][co][lane][c];
+                acc[co][0] += s;
+            }
+        }
+        __syncwarp();
+    }
+    if (x0 + lane < x1) {
+#pragma unroll
+        for (int co = 0; co < kCout; ++co)
+            y[(((long long)n * kCout + co) * H + yy) * W + x0 + lane] = acc[co][0] + (bias ? __ldg(bias + co) : 0.f);
+    }
+}
+
 // out[c] = sum over CTAs of partials[cta * C + c]; block (32 columns, 32 stripes over the CTAs), fixed order, doubles
 __global__ void __launch_bounds__(1024)
 column_sum_kernel(const float* __restrict__ partials, float* __restrict__ out, long long nblk, int C) {
@@ -137,20 +239,38 @@ long long small_wgrad_ctas(int N, int H, int W) {
 
 }  // namespace
 
-extern "C" long long arf_conv3x3_small_wgrad_workspace(int N, int H, int W, int Cin, int Cout) {
+extern "C" int arf_conv3x3_small_fwd(const float* x, const float* w, const float* bias, float* y, int N, int H, int W,
+                                     int Cin, int Cout, void* stream) {
+    ARF_REQUIRE(x && w && y && N > 0 && H > 0 && W > 0);
+    if (Cout != 2 || Cin % 32 != 0 || Cin <= 0) return ARF_EUNSUPPORTED;
+    const int rpr = arf_cdiv(W, kSRun);
+    const long long ctas = ((long long)N * H * rpr + kFWarps - 1) / kFWarps;
+    ARF_REQUIRE(ctas <= 0x7fffffffLL);
+    conv3x3_small_fwd_kernel<2><<<(unsigned)ctas, kFWarps * 32, 0, (cudaStream_t)stream>>>(x, w, bias, y, N, H, W, Cin, rpr);
+    ARF_CHECK_LAUNCH();
+    return ARF_OK;
+}
+
+extern "C" long long arf_conv3x3_small_bwd_workspace(int N, int H, int W, int Cin, int Cout) {
     if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cin % 32 || Cout != 2) return ARF_EINVAL;
     return small_wgrad_ctas(N, H, W) * (Cout * 9LL * Cin + Cout);
 }
 
-extern "C" int arf_conv3x3_small_wgrad(const float* x, const float* gy, float* out, float* partials, int N, int H, int W,
-                                       int Cin, int Cout, void* stream) {
+extern "C" int arf_conv3x3_small_bwd(const float* x, const float* gy, const float* w, float* gx, float* out, float* partials,
+                                     int N, int H, int W, int Cin, int Cout, void* stream) {
     ARF_REQUIRE(x && gy && out && partials && N > 0 && H > 0 && W > 0);
+    ARF_REQUIRE(!gx || w);
     if (Cout != 2 || Cin % 32 != 0 || Cin <= 0) return ARF_EUNSUPPORTED;
     const long long ctas = small_wgrad_ctas(N, H, W);
     ARF_REQUIRE(ctas <= 0x7fffffffLL && Cin / 32 <= 65535);
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid((unsigned)ctas, Cin / 32);
-    conv3x3_small_wgrad_kernel<2><<<grid, kSWarps * 32, 0, st>>>(x, gy, partials, N, H, W, Cin, arf_cdiv(W, kSRun));
+    if (gx)
+        conv3x3_small_bwd_kernel<2, true><<<grid, kSWarps * 32, 0, st>>>(x, gy, w, gx, partials, N, H, W, Cin,
+                                                                          arf_cdiv(W, kSRun));
+    else
+        conv3x3_small_bwd_kernel<2, false><<<grid, kSWarps * 32, 0, st>>>(x, gy, nullptr, nullptr, partials, N, H, W, Cin,
+                                                                           arf_cdiv(W, kSRun));
     ARF_CHECK_LAUNCH();
     const int ctot = Cout * 9 * Cin + Cout;
     column_sum_kernel<<<arf_cdiv(ctot, 32), dim3(32, 32), 0, st>>>(partials, out, ctas, ctot);

@@ -148,9 +148,12 @@ def alg_bytes(name, a):
         return a[9] * a[10] * 40
     if name == "arf_pad_weight":
         return a[6] * a[7] * a[4] * a[5] * 8
-    if name == "arf_conv3x3_small_wgrad":
+    if name == "arf_conv3x3_small_fwd":
         N, Hh, Ww, Ci, Co = a[4:9]
-        return N * Hh * Ww * (Ci + Co) * 4                 # input and output gradient read once
+        return N * Hh * Ww * (Ci + Co) * 4                 # input read once, output written
+    if name == "arf_conv3x3_small_bwd":
+        N, Hh, Ww, Ci, Co = a[6:11]
+        return N * Hh * Ww * (2 * Ci + Co) * 4             # input and output gradient read, input gradient written
     return 0
 
 
@@ -197,9 +200,9 @@ def alg_work(name, a):
     if name in ("arf_bias_leaky_fwd", "arf_bias_leaky_bwd"):
         B, C, HW = a[2:5] if name.endswith("fwd") else a[5:8]
         return "B%d C%d HW%d" % (B, C, HW), 0, 0
-    if name == "arf_conv3x3_small_wgrad":
-        N, Hh, Ww, Ci, Co = a[4:9]
-        return "N%d %dx%d %d->%d" % (N, Hh, Ww, Ci, Co), 2 * N * Hh * Ww * 9 * Ci * Co, 0
+    if name in ("arf_conv3x3_small_fwd", "arf_conv3x3_small_bwd"):
+        N, Hh, Ww, Ci, Co = a[4:9] if name.endswith("fwd") else a[6:11]
+        return "N%d %dx%d %d->%d" % (N, Hh, Ww, Ci, Co), (2 if name.endswith("fwd") else 4) * N * Hh * Ww * 9 * Ci * Co, 0
     return "other", 0, 0
 
 

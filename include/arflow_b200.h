@@ -200,14 +200,18 @@ int arf_bias_leaky_nhwc_bwd_ld(const float* gy, long long gy_ld, const float* y,
 int arf_bias_leaky_nhwc_fwd_ld(const float* src, float* dst, long long dst_ld, const float* bias, long long rows, int C,
                                float slope, void* stream);
 
-/* Weight and bias gradient of the flow-output convolutions, nn.Conv2d(Cin, 2, 3, padding=1) at the end of every
- * decoder level and of the refinement network (models/uflow_model.py:139-143, 232-249), in fp32.
- * x: (N,H,W,Cin) packed channels-last input of the convolution, Cin % 32 == 0; gy: (N,2,H,W) NCHW output gradient.
- * out: 2*9*Cin floats dW in (co, kh, kw, ci) order (= a channels-last (2,Cin,3,3) weight gradient), then 2 floats
- * dbias.  partials: arf_conv3x3_small_wgrad_workspace(...) floats.  Other Cout / Cin: ARF_EUNSUPPORTED. */
-long long arf_conv3x3_small_wgrad_workspace(int N, int H, int W, int Cin, int Cout);
-int arf_conv3x3_small_wgrad(const float* x, const float* gy, float* out, float* partials, int N, int H, int W, int Cin,
-                            int Cout, void* stream);
+/* The flow-output convolutions, nn.Conv2d(Cin, 2, 3, padding=1) at the end of every decoder level and of the
+ * refinement network (models/uflow_model.py:139-143, 232-249), in fp32 on a channels-last input.
+ * x: (N,H,W,Cin) packed channels-last, Cin % 32 == 0; w: (2,3,3,Cin) = a channels-last (2,Cin,3,3) weight;
+ * y / gy: (N,2,H,W) NCHW.  fwd: y = conv(x, w) + bias (bias may be NULL).
+ * bwd: gx (N,H,W,Cin) input gradient (NULL: skipped, then w may be NULL too); out: 2*9*Cin floats dW in
+ * (co, kh, kw, ci) order, then 2 floats dbias; partials: arf_conv3x3_small_bwd_workspace(...) floats.
+ * Other Cout / Cin: ARF_EUNSUPPORTED. */
+int arf_conv3x3_small_fwd(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int Cin,
+                          int Cout, void* stream);
+long long arf_conv3x3_small_bwd_workspace(int N, int H, int W, int Cin, int Cout);
+int arf_conv3x3_small_bwd(const float* x, const float* gy, const float* w, float* gx, float* out, float* partials, int N,
+                          int H, int W, int Cin, int Cout, void* stream);
 
 /* ---------------------------------------------------------------- NHWC concat ---------- */
 /* The decoder's torch.cat([...], dim=1) (models/uflow_model.py:189-205) into a packed NHWC tensor of Cd channels
