@@ -48,6 +48,9 @@ PROTOTYPES = {
     "arf_bias_leaky_nhwc_num_partials": [ctypes.c_longlong, c_int],
     "arf_bias_leaky_nhwc_fwd": [_P, _P, ctypes.c_longlong, c_int, c_float, _P],
     "arf_bias_leaky_nhwc_bwd": [_P, _P, _P, _P, _P, ctypes.c_longlong, c_int, c_float, _P],
+    "arf_conv3x3s2_first_wgrad_workspace": [c_int, c_int, c_int],
+    "arf_conv3x3s2_first_wgrad": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
+    "arf_image_pair_pack": [_P, _P, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, c_float, c_float, _P],
     "arf_conv3x3_small_fwd": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
     "arf_conv3x3_small_bwd_workspace": [c_int, c_int, c_int, c_int, c_int],
     "arf_conv3x3_small_bwd": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
@@ -71,7 +74,8 @@ PROTOTYPES = {
 }
 _RESTYPES = {"arf_error_string": ctypes.c_char_p, "arf_launch_count": ctypes.c_longlong,
              "arf_featnorm_workspace": ctypes.c_longlong, "arf_bias_leaky_num_partials": ctypes.c_longlong, "arf_bias_leaky_nhwc_num_partials": ctypes.c_longlong,
-             "arf_conv3x3_small_bwd_workspace": ctypes.c_longlong}
+             "arf_conv3x3_small_bwd_workspace": ctypes.c_longlong,
+             "arf_conv3x3s2_first_wgrad_workspace": ctypes.c_longlong}
 
 _lib = None
 

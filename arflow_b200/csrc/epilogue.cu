@@ -94,7 +94,7 @@ __global__ void bias_grad_finalize_kernel(const float* __restrict__ partials, fl
 inline int nchunks_of(long long HW) { return (int)((HW + kEChunk - 1) / kEChunk); }
 
 // ---- NHWC (channels-last) variants: y is a (rows = N*H*W) x C row-major matrix --------------------------------
-constexpr int kERows = 256;       // most rows of the matrix one CTA of the backward handles
+constexpr int kERows = 256;       // rows of the matrix one CTA of the backward handles by default
 
 // Rows per CTA of the backward: 256 when that still gives every SM four CTAs, else halved down to 32.  The coarse
 // pyramid levels (49152, 12288, 3072 rows) ran on 192, 48 and 12 CTAs with the fixed 256 and were latency-bound
@@ -102,6 +102,9 @@ constexpr int kERows = 256;       // most rows of the matrix one CTA of the back
 static int nhwc_rows_per_cta(long long rows) {
     int r = kERows;
     while (r > 32 && rows / r < 4LL * ARF_NUM_SMS) r >>= 1;
+    // very tall matrices (786432 rows x 32 channels at pyramid level 0): fewer, longer CTAs as long as eight per SM
+    // remain - the single-CTA-per-32-channels finalize took 16 us for 3072 partial rows
+    while (r < 1024 && rows / (2 * r) >= 8LL * ARF_NUM_SMS) r <<= 1;
     return r;
 }
 

@@ -232,6 +232,92 @@ column_sum_kernel(const float* __restrict__ partials, float* __restrict__ out, l
     }
 }
 
+// ---- weight gradient of the first pyramid convolution --------------------------------------------------------------
+// Conv2d(3, 32, 3, stride 2, padding 1) on the image (models/uflow_model.py:427-436), which the channels-last path
+// stores as 8-channel NHWC pixels (3 real channels, 5 zeros).  2304 outputs over K = N*Ho*Wo = 786432 pixels at
+// chairs_uflow: cuDNN's 64 x 64 wgrad tile takes 197 us, the operands are 200 MB (31 us of HBM time).  lane <-> output
+// channel; a warp walks 32-pixel runs of output rows with the 3 x 3 x 3 input neighbourhood in registers (stride 2:
+// one column carried over, two loaded per pixel as broadcast 16-byte loads).  Only the real input channels get a
+// gradient.  partials[cta][((kh*3 + kw)*3 + ci)*32 + co], then column_sum_kernel.
+constexpr int kFirstCin = 3, kFirstCout = 32, kFirstK = 9 * kFirstCin;
+
+__global__ void __launch_bounds__(kSWarps * 32)
+conv3x3s2_first_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ partials, int Hi,
+                             int Wi, int Ho, int Wo, int runs_per_row, long long nrun) {
+    __shared__ float red[kSWarps][kFirstK][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float acc[9][kFirstCin];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < kFirstCin; ++c) acc[t][c] = 0.f;
+    for (long long run = (long long)blockIdx.x * kSWarps + w; run < nrun; run += (long long)gridDim.x * kSWarps) {
+        const int rx = (int)(run % runs_per_row);
+        const long long t = run / runs_per_row;
+        const int oy = (int)(t % Ho);
+        const long long n = t / Ho;
+        const int ox0 = rx * kSRun, ox1 = ox0 + kSRun < Wo ? ox0 + kSRun : Wo;
+        const float* gr = g + ((n * Ho + oy) * Wo) * kFirstCout + lane;
+        const float* xn = x + n * Hi * Wi * 8;
+        // channels 0..3 of input pixel (2*oy - 1 + r, ix), zero outside the image
+        auto ld = [&](int r, int ix) {
+            const int iy = 2 * oy - 1 + r;
+            const bool ok = iy >= 0 && iy < Hi && ix >= 0 && ix < Wi;
+            return ok ? __ldg(reinterpret_cast<const float4*>(xn + ((long long)iy * Wi + ix) * 8)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        float4 prev[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) prev[r] = ld(r, 2 * ox0 - 1);
+        for (int ox = ox0; ox < ox1; ox += 2) {
+            float gv[2];
+            float4 ca[2][3], cb[2][3];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int px = ox + i;
+                gv[i] = px < ox1 ? __ldg(gr + (long long)px * kFirstCout) : 0.f;    // a zero gradient adds nothing
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    ca[i][r] = ld(r, 2 * px);
+                    cb[i][r] = ld(r, 2 * px + 1);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float4 col[3] = {prev[r], ca[i][r], cb[i][r]};
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        acc[r * 3 + kw][0] = fmaf(gv[i], col[kw].x, acc[r * 3 + kw][0]);
+                        acc[r * 3 + kw][1] = fmaf(gv[i], col[kw].y, acc[r * 3 + kw][1]);
+                        acc[r * 3 + kw][2] = fmaf(gv[i], col[kw].z, acc[r * 3 + kw][2]);
+                    }
+                    prev[r] = cb[i][r];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < kFirstCin; ++c) red[w][t * kFirstCin + c][lane] = acc[t][c];
+    __syncthreads();
+    float* out = partials + (long long)blockIdx.x * (kFirstK * 32);
+    for (int e = threadIdx.x; e < kFirstK * 32; e += kSWarps * 32) {
+        const int r = e >> 5, l = e & 31;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < kSWarps; ++k) s += red[k][r][l];
+        out[e] = s;
+    }
+}
+
+long long first_wgrad_ctas(int N, int Ho, int Wo) {
+    const long long runs = (long long)N * Ho * arf_cdiv(Wo, kSRun);
+    const long long need = (runs + kSWarps - 1) / kSWarps;
+    return need < 4LL * ARF_NUM_SMS ? need : 4LL * ARF_NUM_SMS;
+}
+
 long long small_wgrad_ctas(int N, int H, int W) {
     const long long runs = (long long)N * H * arf_cdiv(W, kSRun);
     return (runs + kSWarps - 1) / kSWarps;
@@ -274,6 +360,28 @@ extern "C" int arf_conv3x3_small_bwd(const float* x, const float* gy, const floa
     ARF_CHECK_LAUNCH();
     const int ctot = Cout * 9 * Cin + Cout;
     column_sum_kernel<<<arf_cdiv(ctot, 32), dim3(32, 32), 0, st>>>(partials, out, ctas, ctot);
+    ARF_CHECK_LAUNCH();
+    return ARF_OK;
+}
+
+extern "C" long long arf_conv3x3s2_first_wgrad_workspace(int N, int Hi, int Wi) {
+    if (N <= 0 || Hi <= 0 || Wi <= 0) return ARF_EINVAL;
+    return first_wgrad_ctas(N, (Hi - 1) / 2 + 1, (Wi - 1) / 2 + 1) * (kFirstK * 32);
+}
+
+extern "C" int arf_conv3x3s2_first_wgrad(const float* x, const float* g, float* out, float* partials, int N, int Hi, int Wi,
+                                         int Cin_real, int Cout, void* stream) {
+    ARF_REQUIRE(x && g && out && partials && N > 0 && Hi > 0 && Wi > 0);
+    if (Cin_real != kFirstCin || Cout != kFirstCout) return ARF_EUNSUPPORTED;
+    ARF_REQUIRE((uintptr_t)x % 16 == 0);
+    const int Ho = (Hi - 1) / 2 + 1, Wo = (Wi - 1) / 2 + 1;
+    const int rpr = arf_cdiv(Wo, kSRun);
+    const long long ctas = first_wgrad_ctas(N, Ho, Wo);
+    cudaStream_t st = (cudaStream_t)stream;
+    conv3x3s2_first_wgrad_kernel<<<(unsigned)ctas, kSWarps * 32, 0, st>>>(x, g, partials, Hi, Wi, Ho, Wo, rpr,
+                                                                          (long long)N * Ho * rpr);
+    ARF_CHECK_LAUNCH();
+    column_sum_kernel<<<arf_cdiv(kFirstK * 32, 32), dim3(32, 32), 0, st>>>(partials, out, ctas, kFirstK * 32);
     ARF_CHECK_LAUNCH();
     return ARF_OK;
 }

@@ -40,7 +40,7 @@ def _int_padding(conv):
 
 class _ConvBiasLeaky(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, padding, dilation, slope):
+    def forward(ctx, x, weight, bias, stride, padding, dilation, slope, real_in=None):
         nhwc = is_nhwc(x)
         y = func.conv2d(x, weight, None, stride, padding, dilation)
         y = y.contiguous(memory_format=CL) if nhwc else y.contiguous()
@@ -54,6 +54,7 @@ class _ConvBiasLeaky(torch.autograd.Function):
                           _lib.stream_ptr())
         ctx.save_for_backward(x, weight, y)
         ctx.cfg = (list(stride), list(padding), list(dilation), float(slope), bias is not None, nhwc)
+        ctx.real_in = real_in
         return y
 
     @staticmethod
@@ -79,15 +80,28 @@ class _ConvBiasLeaky(torch.autograd.Function):
                 _lib.call("arf_bias_leaky_bwd", _lib.dev_ptr(gy, "grad"), _lib.dev_ptr(y), _lib.dev_ptr(g),
                           _lib.dev_ptr(part, allow_none=True), _lib.dev_ptr(db, allow_none=True),
                           B, C, H * W, slope, _lib.stream_ptr())
+        if (nhwc and ctx.real_in == 3 and tuple(weight.shape) == (32, 8, 3, 3) and stride == [2, 2] and padding == [1, 1]
+                and dilation == [1, 1] and not ctx.needs_input_grad[0] and x.dtype == torch.float32):
+            # first pyramid layer on the zero-padded image: arf_conv3x3s2_first_wgrad instead of cuDNN's 64x64 wgrad tile
+            N, _, Hi, Wi = x.shape
+            with torch.cuda.device_of(x):
+                out = torch.empty(27 * 32, dtype=x.dtype, device=x.device)
+                part = torch.empty(lib.arf_conv3x3s2_first_wgrad_workspace(N, Hi, Wi), dtype=x.dtype, device=x.device)
+                _lib.call("arf_conv3x3s2_first_wgrad", x.data_ptr(), g.data_ptr(), out.data_ptr(), part.data_ptr(),
+                          N, Hi, Wi, 3, 32, _lib.stream_ptr())
+                gw = torch.zeros((32, 8, 3, 3), dtype=x.dtype, device=x.device).contiguous(memory_format=CL)
+                gw[:, :3] = out.view(3, 3, 3, 32).permute(3, 2, 0, 1)       # [kh][kw][ci][co] -> (co, ci, kh, kw)
+            return None, gw, db, None, None, None, None, None
         gx, gw, _ = torch.ops.aten.convolution_backward(
             g, x, weight, None, stride, padding, dilation, False, [0, 0], 1,
             [bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1]), False])
-        return gx, gw, db, None, None, None, None
+        return gx, gw, db, None, None, None, None, None
 
 
-def conv_bias_leaky(conv, x, negative_slope, weight=None, bias=None):
+def conv_bias_leaky(conv, x, negative_slope, weight=None, bias=None, real_in=None):
     """leaky_relu(conv(x)) for an nn.Conv2d `conv` (groups 1); `weight` / `bias` override conv.weight / conv.bias
-    (padded / channels-last copies).  CUDA tensors take the fused path; a CPU tensor means the caller is the
+    (padded / channels-last copies).  real_in: number of leading input channels that are not zero padding (the
+    image's 3 of 8 in the first pyramid layer) - the weight gradient of the rest is returned as zero.  CUDA tensors take the fused path; a CPU tensor means the caller is the
     oracle-backed CPU twin of the network (tests, bench.py's cpu_baseline) and gets plain torch."""
     if not x.is_cuda:
         return func.leaky_relu(conv(x), negative_slope=negative_slope)
@@ -97,7 +111,7 @@ def conv_bias_leaky(conv, x, negative_slope, weight=None, bias=None):
     if x.dtype != torch.float32 or w.dtype != torch.float32:
         raise TypeError("conv_bias_leaky: float32 only")
     return _ConvBiasLeaky.apply(x, w, conv.bias if bias is None else bias, tuple(conv.stride),
-                                tuple(_int_padding(conv)), tuple(conv.dilation), negative_slope)
+                                tuple(_int_padding(conv)), tuple(conv.dilation), negative_slope, real_in)
 
 
 class _FlowOutConv(torch.autograd.Function):
@@ -152,6 +166,21 @@ def conv_plain(conv, x, weight=None):
     if _is_flow_out_conv(conv, x, w):
         return _FlowOutConv.apply(x, w, conv.bias)
     return func.conv2d(x, w, conv.bias, conv.stride, _int_padding(conv) if x.is_cuda else conv.padding, conv.dilation)
+
+
+def image_pair_nhwc(pairs, scale=2.0, shift=-1.0):
+    """(B, 6, H, W) image pairs -> the stacked batch [first images; second images] (2B, 8, H, W) channels-last with
+    value * scale + shift on the three real channels and five zero channels (arf_image_pair_pack): the networks' input
+    stage - torch.cat of the two slices, x * 2 - 1, the channels-last pack and its zero tail - in one pass.  No
+    gradient (images are data)."""
+    B, C2, H, W = pairs.shape
+    if C2 != 6 or not pairs.is_cuda or pairs.dtype != torch.float32 or pairs.requires_grad:
+        raise ValueError("image_pair_nhwc: a (B, 6, H, W) float32 CUDA tensor without gradient")
+    with torch.cuda.device_of(pairs):
+        out = torch.empty((2 * B, H, W, 8), dtype=pairs.dtype, device=pairs.device)
+        _lib.call("arf_image_pair_pack", out.data_ptr(), _lib.dev_ptr(pairs.contiguous(), "pairs"), B, H * W, 3, 8,
+                  float(scale), float(shift), _lib.stream_ptr())
+    return out.permute(0, 3, 1, 2)
 
 
 class _BiasAddNhwc(torch.autograd.Function):

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as func
 
-from .fused_conv import (CL, _zeros_cl, conv_transpose_bias, conv_bias_leaky, conv_plain, dense_block_nhwc, nhwc_concat, out_channel_pad,
+from .fused_conv import (CL, _zeros_cl, conv_transpose_bias, image_pair_nhwc, conv_bias_leaky, conv_plain, dense_block_nhwc, nhwc_concat, out_channel_pad,
                          pad_in_channels, pad_weight, to_nchw)
 
 
@@ -193,17 +193,23 @@ class PWCFeaturePyramid(nn.Module):
                 c = out_c
             self._convs.append(group)
 
-    def forward(self, x, split_features_by_sample=False, nhwc=False):
+    def forward(self, x, split_features_by_sample=False, nhwc=False, prepacked=None):
         """nhwc (CUDA only): activations and per-step weight copies are channels-last, so cuDNN's NHWC kernels run
-        without layout conversions; the returned features are channels-last tensors."""
-        x = x * 2. - 1.
-        nhwc = nhwc and x.is_cuda
-        n_pad = 0
-        if nhwc:
-            # 3 image channels -> 8 (zeros): cuDNN's aligned NHWC kernels instead of its 3-channel fallback
-            c_img = x.shape[1]
-            x, _ = nhwc_concat([x])
+        without layout conversions; the returned features are channels-last tensors.
+        prepacked: (tensor, c_img) - the normalised input already as zero-padded channels-last (image_pair_nhwc)."""
+        n_pad, c_img = 0, None
+        if prepacked is not None:
+            x, c_img = prepacked
+            nhwc = True
             n_pad = x.shape[1] - c_img
+        else:
+            x = x * 2. - 1.
+            nhwc = nhwc and x.is_cuda
+            if nhwc:
+                # 3 image channels -> 8 (zeros): cuDNN's aligned NHWC kernels instead of its 3-channel fallback
+                c_img = x.shape[1]
+                x, _ = nhwc_concat([x])
+                n_pad = x.shape[1] - c_img
         features = []
         first = True
         for group in self._convs:
@@ -211,7 +217,8 @@ class PWCFeaturePyramid(nn.Module):
                 w = None
                 if nhwc:
                     w = pad_in_channels(conv.weight, conv.weight.shape[1], n_pad if first else 0)
-                x = conv_bias_leaky(conv, x, self._leaky_relu_alpha, weight=w)
+                x = conv_bias_leaky(conv, x, self._leaky_relu_alpha, weight=w,
+                                    real_in=c_img if (first and n_pad) else None)
                 first = False
             features.append(x)
         if split_features_by_sample:
@@ -401,7 +408,11 @@ class PWCFlow(nn.Module):
         res_dict = {}
         if with_bk and self._stack_directions:
             # one pyramid pass over [img1; img2], one decoder pass over [(1,2); (2,1)]
-            feats = self._feature_pyramid_extractor(torch.cat([x[:, 0:3], x[:, 3:6]], dim=0), nhwc=self._nhwc)
+            if self._nhwc and x.is_cuda and x.dtype == torch.float32 and not x.requires_grad:
+                # cat of the two images, x * 2 - 1 and the 8-channel NHWC pack in one pass
+                feats = self._feature_pyramid_extractor(None, prepacked=(image_pair_nhwc(x), 3))
+            else:
+                feats = self._feature_pyramid_extractor(torch.cat([x[:, 0:3], x[:, 3:6]], dim=0), nhwc=self._nhwc)
             p1 = feats
             if self._nhwc and x.is_cuda:
                 p2 = None       # the half-batch swap rides on the NHWC -> NCHW copy of the features (to_nchw)

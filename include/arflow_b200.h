@@ -213,6 +213,14 @@ long long arf_conv3x3_small_bwd_workspace(int N, int H, int W, int Cin, int Cout
 int arf_conv3x3_small_bwd(const float* x, const float* gy, const float* w, float* gx, float* out, float* partials, int N,
                           int H, int W, int Cin, int Cout, void* stream);
 
+/* Weight gradient of the first pyramid convolution, nn.Conv2d(3, 32, 3, stride=2, padding=1) (models/uflow_model.py:
+ * 427-436), on the 8-channel channels-last image (3 real channels, 5 zeros).  x: (N,Hi,Wi,8); g: (N,Ho,Wo,32)
+ * channels-last gradient of the convolution output, Ho = (Hi-1)/2+1; out: 27*32 floats in [kh][kw][ci][co] order;
+ * partials: arf_conv3x3s2_first_wgrad_workspace(N,Hi,Wi) floats.  Other channel counts: ARF_EUNSUPPORTED. */
+long long arf_conv3x3s2_first_wgrad_workspace(int N, int Hi, int Wi);
+int arf_conv3x3s2_first_wgrad(const float* x, const float* g, float* out, float* partials, int N, int Hi, int Wi,
+                              int Cin_real, int Cout, void* stream);
+
 /* ---------------------------------------------------------------- NHWC concat ---------- */
 /* The decoder's torch.cat([...], dim=1) (models/uflow_model.py:189-205) into a packed NHWC tensor of Cd channels
  * (Cd >= sum of the parts, the tail is padding): pack writes one part at channel offset c_off; src is NHWC
@@ -289,6 +297,13 @@ int arf_resampler_fwd(const float* data, const float* warp_x, const float* warp_
 int arf_resampler_bwd(const float* data, const float* warp_x, const float* warp_y, long long wstride,
                       const float* gout, float* gdata, float* gwx, float* gwy, long long gwstride,
                       int B, int H, int W, int C, long long P, void* stream);
+
+/* Input stage of the stacked-direction networks: src (B, 2C, HW) image pairs -> dst (2B, HW, 8) channels-last,
+ * batch order [first images; second images], value * scale + shift on the C real channels, zeros behind them
+ * (torch.cat of the two slices, x * 2 - 1 and the 3 -> 8 channel pack of models/uflow_model.py:404, 199-205).
+ * Cd must be 8 and C <= 8, else ARF_EUNSUPPORTED. */
+int arf_image_pair_pack(float* dst, const float* src, long long B, long long HW, int C, int Cd, float scale, float shift,
+                        void* stream);
 
 #ifdef __cplusplus
 }

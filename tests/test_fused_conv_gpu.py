@@ -246,3 +246,40 @@ def test_flow_head_conv_gradients_match_torch(shape, bias):
             assert_close(a, b, 1e-4, name)
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+def test_image_pair_pack_is_cat_scale_shift_and_zero_pad():
+    """arf_image_pair_pack == torch.cat([x[:, :3], x[:, 3:]], 0) * 2 - 1 as 8-channel channels-last, bit for bit."""
+    from arflow_b200.fused_conv import image_pair_nhwc, is_nhwc
+    torch.manual_seed(11)
+    x = torch.rand(3, 6, 10, 13, device="cuda")
+    out = image_pair_nhwc(x)
+    ref = torch.cat([x[:, :3], x[:, 3:]], 0) * 2. - 1.
+    assert out.shape == (6, 8, 10, 13) and is_nhwc(out)
+    assert torch.equal(out[:, :3], ref) and float(out[:, 3:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 20, 28), (1, 3, 15, 21), (3, 3, 8, 70)])
+def test_first_pyramid_conv_weight_gradient(shape):
+    """Conv2d(3, 32, 3, stride 2, padding 1) + leaky ReLU on the zero-padded 8-channel image
+    (models/uflow_model.py:427-436): weight / bias gradients of arf_conv3x3s2_first_wgrad + the fused epilogue against
+    torch on the 3-channel image; even and odd sizes, rows longer than one 32-pixel run."""
+    from arflow_b200.fused_conv import conv_bias_leaky, nhwc_concat, pad_in_channels
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(shape[2])
+        conv = nn.Conv2d(3, 32, 3, stride=2, padding=1).cuda()
+        x = torch.randn(shape, device="cuda")
+        ref = func.leaky_relu(conv(x), negative_slope=0.1)
+        w = torch.randn_like(ref)
+        rg = torch.autograd.grad((ref * w).sum(), [conv.weight, conv.bias])
+        x8, _ = nhwc_concat([x])
+        assert x8.shape[1] == 8
+        out = conv_bias_leaky(conv, x8, 0.1, weight=pad_in_channels(conv.weight, 3, 5), real_in=3)
+        og = torch.autograd.grad((out * w).sum(), [conv.weight, conv.bias])
+        assert_close(out, ref, 1e-5, "first conv")
+        assert_close(og[0], rg[0], 1e-4, "dw")
+        assert_close(og[1], rg[1], 1e-4, "db")
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
