@@ -55,12 +55,20 @@ conv3x3_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ 
         const long long row_off = ((long long)n * H + yy) * W * Cin + cg * 32 + lane;
         const float* xr = x + row_off;
         float* gxr = kDgrad ? gx + row_off : nullptr;
-        const float* gyn = gy + (long long)n * kCout * H * W;
-        // gy[n][co][yy + 1 - kh][cx], zero outside the image (the convolution's zero padding seen from the input side)
-        auto ld = [&](int co, int kh, int cx) {
+        // gy[n][co][yy + 1 - kh][cx], zero outside the image (the convolution's zero padding seen from the input
+        // side): one row pointer and validity flag per (co, kh), 32-bit column arithmetic per load
+        const float* gp[kCout][3];
+        bool gok[3];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
             const int ry = yy + 1 - kh;
-            const bool ok = ry >= 0 && ry < H && cx >= 0 && cx < W;
-            return ok ? __ldg(gyn + ((long long)co * H + ry) * W + cx) : 0.f;
+            gok[kh] = ry >= 0 && ry < H;
+#pragma unroll
+            for (int co = 0; co < kCout; ++co)
+                gp[co][kh] = gy + (((long long)n * kCout + co) * H + (gok[kh] ? ry : 0)) * W;
+        }
+        auto ld = [&](int co, int kh, int cx) {
+            return (gok[kh] && (unsigned)cx < (unsigned)W) ? __ldg(gp[co][kh] + cx) : 0.f;
         };
         // window[co][kh][j]: column xx - 1 + j of gy, i.e. kw = 2 - j
         float win[kCout][3][3];
@@ -241,7 +249,7 @@ column_sum_kernel(const float* __restrict__ partials, float* __restrict__ out, l
 // gradient.  partials[cta][((kh*3 + kw)*3 + ci)*32 + co], then column_sum_kernel.
 constexpr int kFirstCin = 3, kFirstCout = 32, kFirstK = 9 * kFirstCin;
 
-__global__ void __launch_bounds__(kSWarps * 32)
+__global__ void __launch_bounds__(kSWarps * 32, 3)
 conv3x3s2_first_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ partials, int Hi,
                              int Wi, int Ho, int Wo, int runs_per_row, long long nrun) {
     __shared__ float red[kSWarps][kFirstK][32];
@@ -258,12 +266,18 @@ conv3x3s2_first_wgrad_kernel(const float* __restrict__ x, const float* __restric
         const long long n = t / Ho;
         const int ox0 = rx * kSRun, ox1 = ox0 + kSRun < Wo ? ox0 + kSRun : Wo;
         const float* gr = g + ((n * Ho + oy) * Wo) * kFirstCout + lane;
-        const float* xn = x + n * Hi * Wi * 8;
-        // channels 0..3 of input pixel (2*oy - 1 + r, ix), zero outside the image
-        auto ld = [&](int r, int ix) {
+        // channels 0..3 of input pixel (2*oy - 1 + r, ix), zero outside the image: one row pointer and one validity
+        // flag per kernel row, 32-bit column arithmetic per load
+        const float4* rp[3];
+        bool rok[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
             const int iy = 2 * oy - 1 + r;
-            const bool ok = iy >= 0 && iy < Hi && ix >= 0 && ix < Wi;
-            return ok ? __ldg(reinterpret_cast<const float4*>(xn + ((long long)iy * Wi + ix) * 8)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rok[r] = iy >= 0 && iy < Hi;
+            rp[r] = reinterpret_cast<const float4*>(x + (n * Hi + (rok[r] ? iy : 0)) * Wi * 8);
+        }
+        auto ld = [&](int r, int ix) {
+            return (rok[r] && (unsigned)ix < (unsigned)Wi) ? __ldg(rp[r] + 2 * ix) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         float4 prev[3];
 #pragma unroll
@@ -315,7 +329,7 @@ conv3x3s2_first_wgrad_kernel(const float* __restrict__ x, const float* __restric
 long long first_wgrad_ctas(int N, int Ho, int Wo) {
     const long long runs = (long long)N * Ho * arf_cdiv(Wo, kSRun);
     const long long need = (runs + kSWarps - 1) / kSWarps;
-    return need < 4LL * ARF_NUM_SMS ? need : 4LL * ARF_NUM_SMS;
+    return need < 3LL * ARF_NUM_SMS ? need : 3LL * ARF_NUM_SMS;   // one resident wave (3 CTAs per SM), grid-stride over runs
 }
 
 long long small_wgrad_ctas(int N, int H, int W) {

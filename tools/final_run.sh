@@ -9,4 +9,3 @@ tail -c 600 gpurun_out/bench_r1_final2.json
 python bench.py --profile-step > gpurun_out/plain_step_final2.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file gpurun_out/launches_step_final2.csv python bench.py --profile-step > gpurun_out/ncu_step_final2.log 2>&1
-bash tools/profile_kernels.sh r1 trisolve
