@@ -55,20 +55,13 @@ conv3x3_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ 
         const long long row_off = ((long long)n * H + yy) * W * Cin + cg * 32 + lane;
         const float* xr = x + row_off;
         float* gxr = kDgrad ? gx + row_off : nullptr;
-        // gy[n][co][yy + 1 - kh][cx], zero outside the image (the convolution's zero padding seen from the input
-        // side): one row pointer and validity flag per (co, kh), 32-bit column arithmetic per load
-        const float* gp[kCout][3];
-        bool gok[3];
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-            const int ry = yy + 1 - kh;
-            gok[kh] = ry >= 0 && ry < H;
-#pragma unroll
-            for (int co = 0; co < kCout; ++co)
-                gp[co][kh] = gy + (((long long)n * kCout + co) * H + (gok[kh] ? ry : 0)) * W;
-        }
+        const float* gyn = gy + (long long)n * kCout * H * W;
+        // gy[n][co][yy + 1 - kh][cx], zero outside the image (the convolution's zero padding seen from the input side).
+        // (Per-(co, kh) row pointers instead of this index arithmetic were slower: 71 vs 59 us at 16 x 96 x 128.)
         auto ld = [&](int co, int kh, int cx) {
-            return (gok[kh] && (unsigned)cx < (unsigned)W) ? __ldg(gp[co][kh] + cx) : 0.f;
+            const int ry = yy + 1 - kh;
+            const bool ok = ry >= 0 && ry < H && cx >= 0 && cx < W;
+            return ok ? __ldg(gyn + ((long long)co * H + ry) * W + cx) : 0.f;
         };
         // window[co][kh][j]: column xx - 1 + j of gy, i.e. kw = 2 - j
         float win[kCout][3][3];
