@@ -250,6 +250,46 @@ def main():
         # fwd: read both maps twice (moments, apply) + write both; bwd: read f, g twice + write both
         report("featnorm_fwd", (16, 32, 96, 128), 16 * n * 4 * 6, 16 * n * 8, *time_graph(mk_norm("fwd"), 16 * n * 24))
         report("featnorm_bwd", (16, 32, 96, 128), 16 * n * 4 * 10, 16 * n * 12, *time_graph(mk_norm("bwd"), 16 * n * 40))
+    if args.what in ("smallconv", "all"):
+        # the own fp32 kernels for the thin convolutions (csrc/smallconv.cu, layout.cu): chairs_uflow level-1 / level-0 shapes
+        N, H, W, Ci = 16, 96, 128, 32
+        px = N * H * W
+
+        def mk_head(kind):
+            def make():
+                x = torch.randn(N, H, W, Ci, device="cuda")
+                w = torch.randn(2, 3, 3, Ci, device="cuda")
+                b = torch.randn(2, device="cuda")
+                y = torch.empty(N, 2, H, W, device="cuda")
+                gy = torch.randn(N, 2, H, W, device="cuda")
+                gx = torch.empty_like(x)
+                out = torch.empty(2 * 9 * Ci + 2, device="cuda")
+                part = torch.empty(lib.arf_conv3x3_small_bwd_workspace(N, H, W, Ci, 2), device="cuda")
+                if kind == "fwd":
+                    return lambda: lib.arf_conv3x3_small_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), N, H, W, Ci, 2, cs())
+                return lambda: lib.arf_conv3x3_small_bwd(x.data_ptr(), gy.data_ptr(), w.data_ptr(), gx.data_ptr(), out.data_ptr(),
+                                                         part.data_ptr(), N, H, W, Ci, 2, cs())
+            return make
+        report("flowhead_fwd", (N, Ci, H, W), px * (Ci + 2) * 4, px * 36 * Ci, *time_graph(mk_head("fwd"), px * (Ci + 2) * 4))
+        report("flowhead_bwd", (N, Ci, H, W), px * (2 * Ci + 2) * 4, px * 72 * Ci, *time_graph(mk_head("bwd"), px * (2 * Ci + 2) * 4))
+        Hi, Wi = 384, 512
+        Ho, Wo = Hi // 2, Wi // 2
+
+        def mk_first():
+            x = torch.randn(N, Hi, Wi, 8, device="cuda")
+            g = torch.randn(N, Ho, Wo, 32, device="cuda")
+            out = torch.empty(27 * 32, device="cuda")
+            part = torch.empty(lib.arf_conv3x3s2_first_wgrad_workspace(N, Hi, Wi), device="cuda")
+            return lambda: lib.arf_conv3x3s2_first_wgrad(x.data_ptr(), g.data_ptr(), out.data_ptr(), part.data_ptr(), N, Hi, Wi, 3, 32, cs())
+        by = N * (Hi * Wi * 8 + Ho * Wo * 32) * 4
+        report("first_wgrad", (N, 8, Hi, Wi), by, N * Ho * Wo * 32 * 54, *time_graph(mk_first, by))
+
+        def mk_pair():
+            src = torch.rand(N // 2, 6, Hi, Wi, device="cuda")
+            dst = torch.empty(N, Hi, Wi, 8, device="cuda")
+            return lambda: lib.arf_image_pair_pack(dst.data_ptr(), src.data_ptr(), N // 2, Hi * Wi, 3, 8, 2.0, -1.0, cs())
+        by = N * Hi * Wi * (3 + 8) * 4
+        report("pair_pack", (N // 2, 6, Hi, Wi), by, 0, *time_graph(mk_pair, by))
     if args.csv:
         os.makedirs(os.path.dirname(args.csv), exist_ok=True)
         with open(args.csv, "w") as f:

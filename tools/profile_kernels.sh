@@ -26,6 +26,9 @@ prof census_bwd census_bwd_kernel census --shapes 8x3x384x512
 prof stencil_fwd 'stencil_mv_kernel' stencil
 prof stencil_bwd 'stencil_mv_bwd_kernel' stencil
 prof trisolve trisolve_scan_kernel stencil
+prof flowhead_fwd conv3x3_small_fwd_kernel smallconv
+prof flowhead_bwd conv3x3_small_bwd_kernel smallconv
+prof first_wgrad conv3x3s2_first_wgrad_kernel smallconv
 prof epilogue_fwd bias_leaky_nhwc_fwd_kernel glue
 prof epilogue_bwd bias_leaky_nhwc_bwd_kernel glue
 prof nhwc_pack nhwc_part_kernel glue
