@@ -31,8 +31,8 @@ PROTOTYPES = {
     "arf_range_map_bwd": [_P, _P, _P] + [c_int] * 4 + [_P],
     "arf_count_to_mask": [_P, _P, ctypes.c_longlong, c_int, c_float, _P],
     "arf_occ_bidir": [_P, _P, _P] + [c_int] * 3 + [c_float, c_float, _P],
-    "arf_resize_bilinear_fwd": [_P, _P, ctypes.c_longlong] + [c_int] * 4 + [c_float] * 3 + [_P],
-    "arf_resize_bilinear_bwd": [_P, _P, ctypes.c_longlong] + [c_int] * 4 + [c_float] * 3 + [_P],
+    "arf_resize_bilinear_fwd": [_P, _P, ctypes.c_longlong] + [c_int] * 4 + [c_float] * 3 + [c_int, _P],
+    "arf_resize_bilinear_bwd": [_P, _P, ctypes.c_longlong] + [c_int] * 4 + [c_float] * 3 + [c_int, _P],
     "arf_census_num_partials": [c_int] * 3,
     "arf_census_fwd": [_P] * 6 + [c_int] * 4 + [c_float] * 3 + [_P],
     "arf_census_bwd": [_P] * 9 + [c_int] * 4 + [c_float] * 3 + [_P],

@@ -61,24 +61,47 @@ class CorrelationFunction(torch.autograd.Function):
 
 
 class Correlation(nn.Module):
-    """`Correlation(pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply)`.
+    """Both reference constructors, told apart by the call form:
 
-    Accepts both reference constructors: the CUDA package's six keyword arguments
-    (correlation.py:48) and correlation_native's `Correlation(max_displacement=4, **kwargs)`
-    (correlation_native.py:7), whose implied geometry is pad=md, kernel 1, strides 1.
+      * CUDA package, correlation.py:48 - `Correlation(pad_size=0, kernel_size=0, max_displacement=0, stride1=1,
+        stride2=2, corr_multiply=1)`: chosen when `pad_size` is passed by keyword or two or more positional arguments
+        are given (what every model does, pwclite.py:124-126).  Its defaults are kept, including stride2=2 and the
+        unusable kernel_size=0 (division by kernel_size**2 * C), which raises at the first forward here.
+      * correlation_native.py:7 - `Correlation(max_displacement=4, *args, **kwargs)`: at most one positional argument
+        and no `pad_size`; every other argument is swallowed as there, geometry pad = md, kernel 1, strides 1.
+
     `corr_multiply` is accepted and ignored, as in the reference kernels.
     """
 
-    def __init__(self, pad_size=None, kernel_size=1, max_displacement=4, stride1=1, stride2=1,
-                 corr_multiply=1):
+    _PKG = ("pad_size", "kernel_size", "max_displacement", "stride1", "stride2", "corr_multiply")
+
+    def __init__(self, *args, **kwargs):
         super().__init__()
-        self.max_displacement = max_displacement
-        self.pad_size = max_displacement if pad_size is None else pad_size
-        self.kernel_size = kernel_size
-        self.stride1 = stride1
-        self.stride2 = stride2
-        self.corr_multiply = corr_multiply
-        self.output_dim = 2 * (max_displacement // stride2) + 1
+        unknown = set(kwargs) - set(self._PKG)
+        if unknown:
+            raise TypeError("Correlation: unexpected arguments %s" % sorted(unknown))
+        if len(args) > len(self._PKG):
+            raise TypeError("Correlation: at most %d positional arguments" % len(self._PKG))
+        if "pad_size" in kwargs or len(args) >= 2:
+            cfg = dict(pad_size=0, kernel_size=0, max_displacement=0, stride1=1, stride2=2, corr_multiply=1)
+            for k, v in zip(self._PKG, args):
+                if k in kwargs:
+                    raise TypeError("Correlation: got multiple values for argument '%s'" % k)
+                cfg[k] = v
+            cfg.update(kwargs)
+        else:
+            md = args[0] if args else kwargs.get("max_displacement", 4)
+            if args and "max_displacement" in kwargs:
+                raise TypeError("Correlation: got multiple values for argument 'max_displacement'")
+            cfg = dict(pad_size=md, kernel_size=1, max_displacement=md, stride1=1, stride2=1,
+                       corr_multiply=kwargs.get("corr_multiply", 1))
+        self.pad_size = cfg["pad_size"]
+        self.kernel_size = cfg["kernel_size"]
+        self.max_displacement = cfg["max_displacement"]
+        self.stride1 = cfg["stride1"]
+        self.stride2 = cfg["stride2"]
+        self.corr_multiply = cfg["corr_multiply"]
+        self.output_dim = 2 * (self.max_displacement // max(self.stride2, 1)) + 1
 
     def forward(self, input1, input2):
         return CorrelationFunction.apply(input1, input2, self.pad_size, self.kernel_size,

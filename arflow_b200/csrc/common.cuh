@@ -4,16 +4,42 @@
 #include <stdint.h>
 #include "../../include/arflow_b200.h"
 
-#define ARF_NUM_SMS 148
+#include <atomic>
+
+// Multiprocessor count of the CURRENT device (148 on a B200), queried once per device: grids are sized from it,
+// and a process may drive several devices (the reference's DataParallel does).
+#define ARF_NUM_SMS arf_num_sms()
+int arf_num_sms();
 
 // number of kernels this library has launched in this process (bench.py reports it as gpu_launches)
-extern long long g_arf_launches;
+extern std::atomic<long long> g_arf_launches;
 
+// Peek, do not get: an error left behind by earlier, unrelated work (cuDNN, NCCL) is reported but stays latched
+// for its owner instead of being cleared here.
 #define ARF_CHECK_LAUNCH()                                   \
     do {                                                     \
-        cudaError_t e__ = cudaGetLastError();                \
+        cudaError_t e__ = cudaPeekAtLastError();             \
         if (e__ != cudaSuccess) return (int)e__;             \
-        ++g_arf_launches;                                    \
+        g_arf_launches.fetch_add(1, std::memory_order_relaxed); \
+    } while (0)
+
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute belongs to (function, device), so the
+// "already done" flag is one bit per device ordinal (devices >= 64 set it on every launch); thread-safe.
+template <typename K>
+static inline cudaError_t arf_ensure_smem(K kern, size_t bytes, std::atomic<unsigned long long>& done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && ((done.load(std::memory_order_acquire) >> dev) & 1ull)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess && dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+    return e;
+}
+#define ARF_ENSURE_SMEM(kern, bytes)                                        \
+    do {                                                                    \
+        static std::atomic<unsigned long long> done__{0};                   \
+        cudaError_t e__ = arf_ensure_smem(kern, bytes, done__);             \
+        if (e__ != cudaSuccess) return (int)e__;                            \
     } while (0)
 
 #define ARF_REQUIRE(cond)                                    \

@@ -507,19 +507,11 @@ int launch_bwd_md4(const float* Fsrc, const float* gout, float* gin, int B, int 
     const float inv_c = 1.0f / (float)C;
     const size_t smem = sizeof(BwdSmem<kSecond>);
     if (tma) {
-        static bool attr = false;
-        if (!attr) {
-            cudaFuncSetAttribute(corr_bwd_md4<kSecond, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr = true;
-        }
+        ARF_ENSURE_SMEM((corr_bwd_md4<kSecond, true>), smem);
         corr_bwd_md4<kSecond, true><<<grid, kBwdThreads, smem, st>>>(mF, mG, Fsrc, gout, gin, B, C, H, W, tiles_x,
                                                                      tiles_y, nsuper, inv_c);
     } else {
-        static bool attr = false;
-        if (!attr) {
-            cudaFuncSetAttribute(corr_bwd_md4<kSecond, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr = true;
-        }
+        ARF_ENSURE_SMEM((corr_bwd_md4<kSecond, false>), smem);
         memset(&mF, 0, sizeof(mF));
         memset(&mG, 0, sizeof(mG));
         corr_bwd_md4<kSecond, false><<<grid, kBwdThreads, smem, st>>>(mF, mG, Fsrc, gout, gin, B, C, H, W, tiles_x,
@@ -544,9 +536,11 @@ int make_geom(CorrGeom& g, int B, int C, int H, int W, int pad, int ks, int md, 
     return ARF_OK;
 }
 
-int g_probe = 0;         // test hook: see corr_fwd_md4
-int g_variant = 0;       // test hook: kernel variant selection while tuning
-int g_force_no_tma = 0;  // test hook: exercise the cp.async producer on TMA-capable shapes
+// Test hooks (arf_debug_set): per calling thread, so concurrent callers (one Python thread per GPU under the
+// reference's DataParallel) never see each other's settings; all default to 0 = production routing.
+thread_local int g_probe = 0;         // see corr_fwd_md4
+thread_local int g_variant = 0;       // kernel variant selection while tuning
+thread_local int g_force_no_tma = 0;  // exercise the cp.async producer on TMA-capable shapes
 
 // The tiled kernels carry a fixed pipeline latency (forward ~11 us, backward ~35 us for any small problem) and, for
 // tensors TMA cannot describe (W % 4 != 0), a single-warp cp.async producer.  Measured with tools/microbench.py
@@ -566,8 +560,8 @@ inline bool is_fast(const CorrGeom& g, bool bwd) {
 
 }  // namespace
 
-extern int g_warp_variant;   // warp.cu
-extern int g_trisolve_variant;   // stencil.cu
+extern thread_local int g_warp_variant;   // warp.cu
+extern thread_local int g_trisolve_variant;   // stencil.cu
 
 extern "C" int arf_debug_set(int key, int value) {
     if (key == 0) { g_force_no_tma = value; return ARF_OK; }
@@ -614,11 +608,7 @@ extern "C" int arf_corr_fwd(const float* f1, const float* f2, float* out, int B,
 #define ARF_LAUNCH_FWD(TMA, RG, STG, MINB, UNR, F2, CC)                                                          \
     do {                                                                                                         \
         auto kern = corr_fwd_md4<TMA, RG, STG, MINB, UNR, F2, CC>;                                               \
-        static bool attr = false;                                                                                \
-        if (!attr) {                                                                                             \
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<RG, CC>(STG)); \
-            attr = true;                                                                                         \
-        }                                                                                                        \
+        ARF_ENSURE_SMEM(kern, (fwd_smem<RG, CC>(STG)));                                                          \
         const int grid = (int)(ntiles < (MINB) * ARF_NUM_SMS ? ntiles : (MINB) * ARF_NUM_SMS);                   \
         kern<<<grid, 32 * (kD * RG + 1), fwd_smem<RG, CC>(STG), st>>>(m1, m2, f1, f2, out, B, C, H, W, tiles_x,  \
                                                                       tiles_y, inv_c, g_probe);                  \

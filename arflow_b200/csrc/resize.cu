@@ -1,6 +1,7 @@
-// Bilinear resize with align_corners=False: upsample / downsample of utils/uflow_utils.py:163-204
-// (F.interpolate with scale_factor, so the source step is exactly 1/scale_factor, ATen
-// area_pixel_compute_scale), optional value scaling for flow fields.
+// Bilinear resize: upsample / downsample of utils/uflow_utils.py:163-204 (align_corners=False; F.interpolate with
+// scale_factor, so the source step is exactly 1/scale_factor, ATen area_pixel_compute_scale) and the flow
+// up-sampling of the PWC-Lite family (models/pwclite.py:178-179, 203: align_corners=True, source step
+// (in-1)/(out-1)); optional value scaling for flow fields.
 #include "common.cuh"
 
 namespace {
@@ -8,12 +9,19 @@ namespace {
 struct ResizeGeom {
     int N, Hi, Wi, Ho, Wo;
     float rh, rw, mul;
+    int align;
 };
 
-__device__ __forceinline__ void src_index(int dst, float r, int in_size, int& i0, int& i1, float& l0, float& l1) {
-    // ATen area_pixel_compute_source_index (align_corners=False, non-cubic): clamp below at 0
-    float s = r * ((float)dst + 0.5f) - 0.5f;
-    s = s < 0.f ? 0.f : s;
+__device__ __forceinline__ void src_index(int dst, float r, int in_size, int align, int& i0, int& i1, float& l0,
+                                          float& l1) {
+    // ATen area_pixel_compute_source_index (non-cubic): align_corners=True -> r*dst; False -> clamp below at 0
+    float s;
+    if (align) {
+        s = r * (float)dst;
+    } else {
+        s = r * ((float)dst + 0.5f) - 0.5f;
+        s = s < 0.f ? 0.f : s;
+    }
     i0 = (int)s;
     if (i0 > in_size - 1) i0 = in_size - 1;
     i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
@@ -32,8 +40,8 @@ __global__ void __launch_bounds__(256) resize_fwd_kernel(const float* __restrict
             const unsigned oy = idx / (unsigned)g.Wo, ox = idx - oy * (unsigned)g.Wo;
             int y0, y1, x0, x1;
             float hy0, hy1, wx0, wx1;
-            src_index((int)oy, g.rh, g.Hi, y0, y1, hy0, hy1);
-            src_index((int)ox, g.rw, g.Wi, x0, x1, wx0, wx1);
+            src_index((int)oy, g.rh, g.Hi, g.align, y0, y1, hy0, hy1);
+            src_index((int)ox, g.rw, g.Wi, g.align, x0, x1, wx0, wx1);
             const float* r0 = p + (size_t)y0 * g.Wi;
             const float* r1 = p + (size_t)y1 * g.Wi;
             float v = hy0 * (wx0 * __ldg(r0 + x0) + wx1 * __ldg(r0 + x1)) + hy1 * (wx0 * __ldg(r1 + x0) + wx1 * __ldg(r1 + x1));
@@ -55,10 +63,12 @@ __global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict
             const int iy = (int)(idx / (unsigned)g.Wi), ix = (int)(idx - (unsigned)iy * (unsigned)g.Wi);
             // exact range is [ceil(lo), ceil(hi) - 1]; floor/ceil leave one candidate of slack on each side against
             // rounding, candidates that do not reference the pixel get weight 0 below
-            int oy_lo = max(0, (int)floorf(((float)iy - 0.5f) * inv_rh - 0.5f));
-            int oy_hi = min(g.Ho - 1, (int)ceilf(((float)iy + 1.5f) * inv_rh - 0.5f));
-            int ox_lo = max(0, (int)floorf(((float)ix - 0.5f) * inv_rw - 0.5f));
-            int ox_hi = min(g.Wo - 1, (int)ceilf(((float)ix + 1.5f) * inv_rw - 0.5f));
+            // (align_corners=True: source = r*dst, so dst in ((iy-1)/r, (iy+1)/r); same slack)
+            const float sh = g.align ? 0.f : 0.5f;
+            int oy_lo = max(0, (int)floorf(((float)iy - 1.f + sh) * inv_rh - sh) - (g.align ? 1 : 0));
+            int oy_hi = min(g.Ho - 1, (int)ceilf(((float)iy + 1.f + sh) * inv_rh - sh) + (g.align ? 1 : 0));
+            int ox_lo = max(0, (int)floorf(((float)ix - 1.f + sh) * inv_rw - sh) - (g.align ? 1 : 0));
+            int ox_hi = min(g.Wo - 1, (int)ceilf(((float)ix + 1.f + sh) * inv_rw - sh) + (g.align ? 1 : 0));
             if (iy == 0) oy_lo = 0;            // rows clamped at the top edge all read row 0
             if (ix == 0) ox_lo = 0;
             if (iy == g.Hi - 1) oy_hi = g.Ho - 1;
@@ -67,14 +77,14 @@ __global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict
             for (int oy = oy_lo; oy <= oy_hi; ++oy) {
                 int y0, y1;
                 float hy0, hy1;
-                src_index(oy, g.rh, g.Hi, y0, y1, hy0, hy1);
+                src_index(oy, g.rh, g.Hi, g.align, y0, y1, hy0, hy1);
                 float wy = (y0 == iy ? hy0 : 0.f) + (y1 == iy ? hy1 : 0.f);
                 if (wy == 0.f) continue;
                 float row = 0.f;
                 for (int ox = ox_lo; ox <= ox_hi; ++ox) {
                     int x0, x1;
                     float wx0, wx1;
-                    src_index(ox, g.rw, g.Wi, x0, x1, wx0, wx1);
+                    src_index(ox, g.rw, g.Wi, g.align, x0, x1, wx0, wx1);
                     float wx = (x0 == ix ? wx0 : 0.f) + (x1 == ix ? wx1 : 0.f);
                     if (wx != 0.f) row = fmaf(wx, __ldg(go + (size_t)oy * g.Wo + ox), row);
                 }
@@ -95,9 +105,12 @@ static inline dim3 resize_grid(long long pix_per_plane, long long planes) {
     return dim3((unsigned)bx, (unsigned)by);
 }
 
-int make_geom(ResizeGeom& g, long long N, int Hi, int Wi, int Ho, int Wo, float rh, float rw, float mul) {
+int make_geom(ResizeGeom& g, long long N, int Hi, int Wi, int Ho, int Wo, float rh, float rw, float mul, int align) {
+    // align_corners=True with a single output row / column has source step 0 (ATen); the gather backward divides by
+    // the step, so that degenerate case is refused
     if (N <= 0 || N > 0x7fffffffLL || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0 || !(rh > 0.f) || !(rw > 0.f))
         return ARF_EINVAL;
+    g.align = align ? 1 : 0;
     if ((long long)Hi * Wi > 0x7fffffffLL || (long long)Ho * Wo > 0x7fffffffLL) return ARF_EINVAL;
     g.N = (int)N; g.Hi = Hi; g.Wi = Wi; g.Ho = Ho; g.Wo = Wo; g.rh = rh; g.rw = rw; g.mul = mul;
     return ARF_OK;
@@ -106,10 +119,10 @@ int make_geom(ResizeGeom& g, long long N, int Hi, int Wi, int Ho, int Wo, float 
 }  // namespace
 
 extern "C" int arf_resize_bilinear_fwd(const float* in, float* out, long long planes, int Hi, int Wi, int Ho, int Wo,
-                                       float rh, float rw, float mul, void* stream) {
+                                       float rh, float rw, float mul, int align_corners, void* stream) {
     ARF_REQUIRE(in && out);
     ResizeGeom g;
-    int rc = make_geom(g, planes, Hi, Wi, Ho, Wo, rh, rw, mul);
+    int rc = make_geom(g, planes, Hi, Wi, Ho, Wo, rh, rw, mul, align_corners);
     if (rc) return rc;
     resize_fwd_kernel<<<resize_grid((long long)Ho * Wo, planes), 256, 0, (cudaStream_t)stream>>>(in, out, g);
     ARF_CHECK_LAUNCH();
@@ -117,10 +130,10 @@ extern "C" int arf_resize_bilinear_fwd(const float* in, float* out, long long pl
 }
 
 extern "C" int arf_resize_bilinear_bwd(const float* gout, float* gin, long long planes, int Hi, int Wi, int Ho,
-                                       int Wo, float rh, float rw, float mul, void* stream) {
+                                       int Wo, float rh, float rw, float mul, int align_corners, void* stream) {
     ARF_REQUIRE(gout && gin);
     ResizeGeom g;
-    int rc = make_geom(g, planes, Hi, Wi, Ho, Wo, rh, rw, mul);
+    int rc = make_geom(g, planes, Hi, Wi, Ho, Wo, rh, rw, mul, align_corners);
     if (rc) return rc;
     resize_bwd_kernel<<<resize_grid((long long)Hi * Wi, planes), 256, 0, (cudaStream_t)stream>>>(gout, gin, g);
     ARF_CHECK_LAUNCH();

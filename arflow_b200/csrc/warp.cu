@@ -24,7 +24,7 @@
 // atomics saved; 32-bit tap offsets with advancing plane pointers: slower (84 vs 74 us forward).
 #include "common.cuh"
 
-int g_warp_variant = 0;   // test hook (arf_debug_set key 3): 1 = force the direct kernels, 2 = force the window kernels
+thread_local int g_warp_variant = 0;   // test hook, per calling thread (arf_debug_set key 3): 1 = force the direct kernels, 2 = force the window kernels
 
 namespace {
 
@@ -801,15 +801,15 @@ extern "C" int arf_warp_bwd(const float* x, const float* field, const float* gy,
         const int tiles_x = arf_cdiv(Wo, kWTW), tiles_y = arf_cdiv(Ho, 4 * P);
         const long long ntiles = (long long)tiles_x * tiles_y * B;
         if (ntiles <= 0x7fffffffLL) {
-            static bool attr = false;
-            if (!attr) {
-#define ARF_WIN_ATTR(PP)                                                                                              \
-    cudaFuncSetAttribute(warp_gfield_win<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmem);             \
-    cudaFuncSetAttribute(warp_gx_csr<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GxSmem<PP>))
-                ARF_WIN_ATTR(4); ARF_WIN_ATTR(2); ARF_WIN_ATTR(1);
+#define ARF_WIN_ATTR(PP)                                                                \
+    do {                                                                                \
+        ARF_ENSURE_SMEM(warp_gfield_win<PP>, kWinSmem);                                 \
+        ARF_ENSURE_SMEM(warp_gx_csr<PP>, sizeof(GxSmem<PP>));                           \
+    } while (0)
+            if (P == 4) ARF_WIN_ATTR(4);
+            else if (P == 2) ARF_WIN_ATTR(2);
+            else ARF_WIN_ATTR(1);
 #undef ARF_WIN_ATTR
-                attr = true;
-            }
             const int vec = ((uintptr_t)x % 16 == 0) && (Ws % 4 == 0);
             const int vec_out = ((uintptr_t)gy % 16 == 0) && (Wo % 4 == 0);
 #define ARF_WIN_LAUNCH(PP)                                                                                             \

@@ -26,7 +26,7 @@ import torch.distributed as dist
 
 class UFlowTrainStep:
     def __init__(self, model, loss_fn, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, use_graph=True, world_size=1,
-                 n_buckets=3, global_census_norm=False):
+                 n_buckets=3, global_census_norm=False, allreduce="auto"):
         if global_census_norm and world_size > 1:
             # batch-global census normaliser: one more collective inside the forward pass,
             # which rules out the captured fwd+bwd graph on this pool
@@ -38,6 +38,7 @@ class UFlowTrainStep:
         self.loss_fn = loss_fn
         self.world_size = world_size
         self.use_graph = use_graph
+        self.allreduce_mode = None if world_size == 1 else "nccl"
         self.params = [p for p in model.parameters() if p.requires_grad]
         dev = self.params[0].device
         if dev.type == "cuda" and getattr(model, "_nhwc", False):
@@ -128,10 +129,6 @@ class UFlowTrainStep:
             for b in range(len(self._buckets)):
                 self._launch_allreduce(b)
             self._counts = [sum(1 for i in self._seen if self._bucket_of[i] == b) for b in range(len(self._buckets))]
-        else:
-            for b, c in enumerate(self._counts):
-                if c == 0:               # a bucket made only of gradient-less parameters: nothing to wait for
-                    pass
         if self._on_cuda:
             torch.cuda.current_stream().wait_stream(self._comm_stream)
 
@@ -197,4 +194,5 @@ class UFlowTrainStep:
         if self.world_size > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
             self._graph_opt.replay()
-        return self._static_out
+        # a copy: the graph overwrites its static output on the next replay, a caller may keep the returned tensor
+        return self._static_out.clone()

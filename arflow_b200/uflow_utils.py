@@ -58,14 +58,17 @@ def mask_invalid(coords):
 
 
 class _RangeMapFunction(torch.autograd.Function):
+    """Forward splat count; `kind` 0 = the field is a flow (base grid added), 1 = absolute (x, y) coordinates."""
+
     @staticmethod
-    def forward(ctx, flow):
+    def forward(ctx, flow, kind=0):
         flow = flow.contiguous()
         B, _, H, W = flow.shape
         with torch.cuda.device_of(flow):
             count = _new_like(flow, (B, 1, H, W))
-            _lib.call("arf_range_map", _lib.dev_ptr(flow, "flow"), _lib.dev_ptr(count), B, H, W, 0, _lib.stream_ptr())
+            _lib.call("arf_range_map", _lib.dev_ptr(flow, "flow"), _lib.dev_ptr(count), B, H, W, kind, _lib.stream_ptr())
         ctx.save_for_backward(flow)
+        ctx.kind = kind
         return count
 
     @staticmethod
@@ -76,8 +79,8 @@ class _RangeMapFunction(torch.autograd.Function):
         with torch.cuda.device_of(flow):
             gflow = torch.empty_like(flow)
             _lib.call("arf_range_map_bwd", _lib.dev_ptr(flow), _lib.dev_ptr(gcount, "grad"), _lib.dev_ptr(gflow),
-                      B, H, W, 0, _lib.stream_ptr())
-        return gflow
+                      B, H, W, ctx.kind, _lib.stream_ptr())
+        return gflow, None
 
 
 def compute_range_map(flow):
@@ -101,10 +104,10 @@ def clamp01(count, mode=0, th=0.0):
 # --------------------------------------------------------------------------- resize --------
 class _ResizeFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, img, Ho, Wo, rh, rw, mul):
+    def forward(ctx, img, Ho, Wo, rh, rw, mul, align=0):
         img = img.contiguous()
         B, C, Hi, Wi = img.shape
-        args = (B * C, Hi, Wi, Ho, Wo, float(rh), float(rw), float(mul))
+        args = (B * C, Hi, Wi, Ho, Wo, float(rh), float(rw), float(mul), int(align))
         with torch.cuda.device_of(img):
             out = _new_like(img, (B, C, Ho, Wo))
             _lib.call("arf_resize_bilinear_fwd", _lib.dev_ptr(img, "img"), _lib.dev_ptr(out), *args, _lib.stream_ptr())
@@ -119,7 +122,22 @@ class _ResizeFunction(torch.autograd.Function):
             gin = _new_like(gout, ctx.in_shape)
             _lib.call("arf_resize_bilinear_bwd", _lib.dev_ptr(gout, "grad"), _lib.dev_ptr(gin), *ctx.args,
                       _lib.stream_ptr())
-        return gin, None, None, None, None, None
+        return gin, None, None, None, None, None, None
+
+
+def interpolate_align_corners(img, scale_factor, mul=1.0):
+    """mul * F.interpolate(img, scale_factor=s, mode='bilinear', align_corners=True): the flow up-sampling of the
+    PWC-Lite family (models/pwclite.py:178-179, 203; `mul` folds the `flow * s` in)."""
+    import math
+    _, _, H, W = img.shape
+    Ho, Wo = int(math.floor(H * scale_factor)), int(math.floor(W * scale_factor))
+    if Ho < 2 or Wo < 2 or H < 2 or W < 2:
+        raise ValueError("interpolate_align_corners: needs at least 2 rows and columns on both sides")
+    # ATen area_pixel_compute_scale: float(in - 1) / (out - 1), one fp32 rounding
+    import numpy as np
+    rh = float(np.float32(H - 1) / np.float32(Ho - 1))
+    rw = float(np.float32(W - 1) / np.float32(Wo - 1))
+    return _ResizeFunction.apply(img, Ho, Wo, rh, rw, mul, 1)
 
 
 def _interpolate(img, scale_factor, mul):

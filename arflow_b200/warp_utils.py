@@ -83,12 +83,9 @@ def norm_grid(v_grid):
 
 
 def _splat(field, kind):
-    field = field.detach().contiguous()
-    B, _, H, W = field.shape
-    with torch.cuda.device_of(field):
-        count = torch.empty((B, 1, H, W), dtype=field.dtype, device=field.device)
-        _lib.call("arf_range_map", _lib.dev_ptr(field, "flow"), _lib.dev_ptr(count), B, H, W, kind, _lib.stream_ptr())
-    return count
+    # differentiable in the field like the reference's scatter_add of bilinear weights (warp_utils.py:60-78, 222-238)
+    from .uflow_utils import _RangeMapFunction
+    return _RangeMapFunction.apply(field, kind)
 
 
 def get_corresponding_map(data):

@@ -121,13 +121,14 @@ int arf_occ_bidir(const float* flow12, const float* flow21_warped, float* out, i
                   float scale, float bias, void* stream);
 
 /* ---------------------------------------------------------------- bilinear resize ------ */
-/* F.interpolate(mode='bilinear', align_corners=False) as used by upsample/downsample (uflow_utils.py:163-204):
- * rh, rw = source step per destination pixel (= 1/scale_factor), out = mul * interp (mul scales flow values).
- * in: (planes,Hi,Wi) -> out: (planes,Ho,Wo).  The backward is a deterministic gather. */
+/* F.interpolate(mode='bilinear'): align_corners=0 as used by upsample/downsample (uflow_utils.py:163-204), rh, rw =
+ * source step per destination pixel (= 1/scale_factor); align_corners=1 as used by the PWC-Lite flow up-sampling
+ * (models/pwclite.py:178-179, 203), rh = (Hi-1)/(Ho-1), rw = (Wi-1)/(Wo-1).  out = mul * interp (mul scales flow
+ * values).  in: (planes,Hi,Wi) -> out: (planes,Ho,Wo).  The backward is a deterministic gather. */
 int arf_resize_bilinear_fwd(const float* in, float* out, long long planes, int Hi, int Wi, int Ho, int Wo,
-                            float rh, float rw, float mul, void* stream);
+                            float rh, float rw, float mul, int align_corners, void* stream);
 int arf_resize_bilinear_bwd(const float* gout, float* gin, long long planes, int Hi, int Wi, int Ho, int Wo,
-                            float rh, float rw, float mul, void* stream);
+                            float rh, float rw, float mul, int align_corners, void* stream);
 
 /* ---------------------------------------------------------------- census / ternary ----- */
 /* Number of per-CTA partial sums (2 floats each) the fused reduction needs for a (B,3,H,W) image pair. */

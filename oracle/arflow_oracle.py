@@ -351,7 +351,7 @@ def uflow_loss(output, target, w_census=1.0, w_smooth=4.0, edge_constant=150.0, 
 
 # --------------------------------------------------------------------------- CPU train step -
 class OracleOps:
-    """CPU twins of the ops arflow_b200.uflow_model.PWCFlow calls (its `ops` argument)."""
+    """The oracle's hot-path ops under the names the reference's PWCFlow calls them by (uflow_utils.*)."""
     flow_to_warp = staticmethod(flow_to_warp)
 
     @staticmethod
@@ -368,18 +368,15 @@ class OracleOps:
 
 
 class CpuTrainStep:
-    """The reference's chairs_uflow training step restated on the CPU (PWCFlow + UFlowLoss + Adam,
-    trainer/uflow_trainer.py:30-73, configs/chairs_uflow.json) with the oracle's hot-path ops: the
-    baseline bench.py times beside the B200 numbers.  The network definition (plain nn.Conv2d layers)
-    is shared with the product; the hot path is not."""
+    """The reference's UFlow training step restated on the CPU (PWCFlow + UFlowLoss + Adam,
+    trainer/uflow_trainer.py:30-73, configs/chairs_uflow.json / kitti_uflow.json): the baseline bench.py times
+    beside the B200 numbers.  Network = oracle/cpu_nets.PWCFlowCPU (a restatement of models/uflow_model.py, no
+    arflow_b200 code), hot path = this file."""
 
     def __init__(self, level_dropout=0.1, feature_norm=True, smooth_order=1, lr=1e-4, seed=0):
-        import types
-        from arflow_b200.uflow_model import PWCFlow
+        from .cpu_nets import PWCFlowCPU
         torch.manual_seed(seed)
-        cfg = types.SimpleNamespace(level_dropout=level_dropout, feature_norm=feature_norm)
-        self.model = PWCFlow(cfg, ops=OracleOps(), stack_directions=False)
-        self.model.init_weights()   # no-op, like the reference's
+        self.model = PWCFlowCPU(level_dropout=level_dropout, feature_norm=feature_norm)
         self.model.train()
         self.smooth_order = smooth_order
         self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-8)
@@ -393,6 +390,20 @@ class CpuTrainStep:
         out[0].backward()
         self.opt.step()
         return float(out[0].detach())
+
+
+class CpuPwcLiteInference:
+    """Config 1 on the CPU: PWCLite(upsample=True, n_frames=2, reduce_dense=True) two-view inference through
+    `correlation_native` + `flow_warp` (models/pwclite.py:260-283, restated in oracle/cpu_nets.PWCLiteCPU)."""
+
+    def __init__(self, seed=0):
+        from .cpu_nets import PWCLiteCPU
+        torch.manual_seed(seed)
+        self.model = PWCLiteCPU(upsample=True, n_frames=2, reduce_dense=True).eval()
+
+    def __call__(self, img_pair):
+        with torch.no_grad():
+            return self.model(img_pair, with_bk=False)['flows_fw'][0]
 
 
 # --------------------------------------------------------------------------- triangular -----

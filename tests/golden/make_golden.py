@@ -283,10 +283,77 @@ def prob_model():
               "keys": np.asarray(list(net.state_dict().keys()))})
 
 
+def round2():
+    """Fixtures added in round 2 (own generators, so the files above are unchanged): normalize_features,
+    align_corners=True flow up-sampling, a larger inverse-diagonal case, the PWC-Lite network."""
+    from easydict import EasyDict
+    gen = torch.Generator().manual_seed(2024)
+
+    # ---- normalize_features (uflow_model.py:8-50), the setting PWCFlow uses + two other switch combinations ----
+    from models.uflow_model import normalize_features
+    f1, f2 = rnd(gen, 2, 6, 9, 11, scale=1.7) + 0.3, rnd(gen, 2, 6, 9, 11, scale=0.6) - 0.2
+    res = {}
+    for tag, kw in (("all", dict(normalize=True, center=True, moments_across_channels=True, moments_across_images=True)),
+                    ("perimg", dict(normalize=True, center=True, moments_across_channels=True, moments_across_images=False)),
+                    ("perch", dict(normalize=True, center=False, moments_across_channels=False, moments_across_images=True))):
+        for k, v in both(lambda a, b: tuple(normalize_features([a, b], **kw)), f1, f2, grads=(0, 1)).items():
+            res["%s_%s" % (tag, k)] = v
+    save("normalize_features", (f1, f2), res)
+
+    # ---- F.interpolate(flow * s, scale_factor=s, bilinear, align_corners=True) (pwclite.py:178-179, 203) ----
+    import torch.nn.functional as F
+    flow = rnd(gen, 2, 2, 6, 10, scale=2.0)
+    res = {}
+    for s in (2, 4):
+        for k, v in both(lambda a: F.interpolate(a * s, scale_factor=s, mode='bilinear', align_corners=True), flow,
+                         grads=(0,)).items():
+            res["up%d_%s" % (s, k)] = v
+    save("resize_align_corners", (flow,), res)
+
+    # ---- inverse diagonal, larger than the 4x5 case of `triag` (marginal variances, triag_solve.py:205-218) ----
+    from utils import triag_solve as ts
+    a = 1.0 + rnd(gen, 2, 2, 12, 17, uniform=True)
+    b, c = rnd(gen, 2, 2, 12, 16, scale=0.4), rnd(gen, 2, 2, 11, 17, scale=0.4)
+
+    def marginal(a, b, c):
+        Hh = torch.zeros_like(a)
+        d0 = torch.zeros_like(a[:, :, :-1, :-1])
+        for i in range(a.shape[2]):
+            for j in range(a.shape[3]):
+                e = torch.zeros_like(a)
+                e[:, :, i, j] = 1
+                y = ts.forward_substitution(a, b, c, d0, e)
+                Hh[:, :, i, j] = torch.sum(y * y, dim=(2, 3))
+        return Hh
+    save("invdiag_12x17", (a, b, c), both(marginal, a, b, c))
+
+    # ---- PWCLite (config 1's network): eval mode, PyTorch default init in construction order ----
+    from models.pwclite import PWCLite
+    for tag, cfg, seed, shape in (("pwclite_eval", EasyDict(upsample=True, n_frames=2, reduce_dense=True), 511, (1, 6, 128, 192)),
+                                  ("pwclite3_eval", EasyDict(upsample=True, n_frames=3, reduce_dense=False), 512, (1, 9, 128, 128))):
+        torch.manual_seed(seed)
+        net = PWCLite(cfg)
+        net.init_weights()          # a no-op in the reference (iterates (name, module) tuples)
+        net.eval()
+        x = torch.rand(*shape, generator=torch.Generator().manual_seed(seed + 1000))   # regenerated by the test
+        with torch.no_grad():
+            r = net(x, with_bk=True)
+        out = {"n_params": np.asarray(sum(p.numel() for p in net.parameters())),
+               "keys": np.asarray(list(net.state_dict().keys())), "shape": np.asarray(shape)}
+        for d in ("flows_fw", "flows_bw"):
+            for i in (1, 3, len(r[d]) - 1):      # two-frame: 1/4, 1/16, 1/64 resolution
+                out["%s%d" % (d[6:], i)] = r[d][i].numpy()
+            out["%s0_absmean" % d[6:]] = np.asarray(r[d][0].abs().mean().item())
+        save(tag, (np.asarray(seed),), out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     if len(sys.argv) > 1 and sys.argv[1] == "probflow":
         prob_model()
+    elif len(sys.argv) > 1 and sys.argv[1] == "round2":
+        round2()
     else:
         main()
         prob_model()
+        round2()

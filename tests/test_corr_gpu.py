@@ -101,3 +101,25 @@ def test_cp_async_staging_path_matches_tma_path(oracle, shape):
     assert torch.equal(a, b)
     assert_close(a, oracle.corr_fwd_c(f1.cpu(), f2.cpu()), RTOL_VALUE)
 
+
+
+# Full BASELINE sizes against the C oracle (double accumulation): config 2's finest level, and batch 16 at the
+# channel counts / pyramid levels of the PWC-Lite family (models/pwclite.py:113: C = 64, 96, 128, 192 at 1/8 .. 1/64
+# of 384x512) plus config 1's own level shapes.
+@pytest.mark.parametrize("shape", [(8, 32, 96, 128), (16, 64, 48, 64), (16, 96, 24, 32), (16, 128, 12, 16),
+                                   (16, 192, 6, 8), (1, 192, 6, 10), (1, 128, 12, 20), (1, 96, 24, 40),
+                                   (1, 64, 48, 80), (1, 32, 96, 160)])
+def test_full_size_vs_oracle(oracle, shape):
+    gen = torch.Generator().manual_seed(sum(shape))
+    f1, f2 = torch.randn(shape, generator=gen), torch.randn(shape, generator=gen)
+    ref = oracle.corr_fwd_c(f1, f2)
+    w = torch.randn(ref.shape, generator=gen)
+    r1, r2 = oracle.corr_bwd_c(f1, f2, w)
+    out, g1, g2 = _run(f1, f2, w, pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1)
+    assert_close(out, ref, RTOL_VALUE, "cost volume")
+    assert_close(g1, r1, RTOL_GRAD, "grad f1")
+    assert_close(g2, r2, RTOL_GRAD, "grad f2")
+    # second, element-wise check with an absolute floor: |a - ref| <= rtol * (|ref| + rms(ref))
+    rms = ref.double().pow(2).mean().sqrt().item()
+    err = (out.detach().double().cpu() - ref.double()).abs()
+    assert bool((err <= 1e-5 * (ref.double().abs() + rms)).all()), "element-wise: max %.3e" % err.max().item()

@@ -53,6 +53,109 @@ def time_graph(make_call, set_bytes, reps=3):
     return ts[len(ts) // 2], ts[0]
 
 
+def time_eager(fn, reps=10):
+    """Comparator timing for multi-launch ATen paths (not graph-capturable as written): CUDA events around `reps` eager
+    calls after two warm-up calls, L2 flushed before each by writing a 256 MB buffer outside the events."""
+    flush = torch.empty(64 * 1024 * 1024, device="cuda")
+    fn(); fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) * 1e-3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def load_ref_cuda():
+    """The reference's own CUDA correlation package, compiled unmodified for sm_100a (oracle/build_ref.py)."""
+    import importlib.util
+    so = os.path.join(ROOT, "oracle", "_ref", "correlation_cuda.so")
+    if not os.path.exists(so):
+        return None
+    spec = importlib.util.spec_from_file_location("correlation_cuda", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def native_cost_volume(x1, x2, md=4):
+    """models/correlation_native.py:13-23 as written (81 shifted products + channel mean + cat) - the ATen comparator."""
+    pad = torch.nn.functional.pad(x2, [md] * 4)
+    H, W = x1.shape[2:]
+    cv = []
+    for i in range(2 * md + 1):
+        for j in range(2 * md + 1):
+            cv.append(torch.mean(x1 * pad[:, :, i:i + H, j:j + W], 1, keepdim=True))
+    return torch.cat(cv, 1)
+
+
+def grid_sample_warp(x, flow):
+    """utils/warp_utils.py:83-90 with the base grid already on the device (the reference builds it on the host per call)."""
+    B, _, H, W = flow.shape
+    jj = torch.arange(W, device=x.device, dtype=x.dtype).view(1, 1, 1, W).expand(B, 1, H, W)
+    ii = torch.arange(H, device=x.device, dtype=x.dtype).view(1, 1, H, 1).expand(B, 1, H, W)
+    v = torch.cat([jj, ii], 1) + flow
+    g = torch.stack([2.0 * v[:, 0] / (W - 1) - 1.0, 2.0 * v[:, 1] / (H - 1) - 1.0], -1)
+    return torch.nn.functional.grid_sample(x, g, mode="bilinear", padding_mode="zeros", align_corners=True)
+
+
+def comparators(shapes, rows_out):
+    """BASELINE.md §2 comparators on the same GPU: (i) the reference's Python/ATen path (correlation_native, grid_sample),
+    (ii) the reference's own correlation_cuda rebuilt for sm_100a; next to the arf_* calls."""
+    from arflow_b200 import _lib
+    lib = _lib.load()
+    ref = load_ref_cuda()
+    cs = lambda: torch.cuda.current_stream().cuda_stream
+    for (B, C, H, W) in shapes:
+        f1 = torch.randn(B, C, H, W, device="cuda")
+        f2 = torch.randn(B, C, H, W, device="cuda")
+        go = torch.randn(B, 81, H, W, device="cuda")
+        out = torch.empty(B, 81, H, W, device="cuda")
+        g1, g2 = torch.empty_like(f1), torch.empty_like(f2)
+        fl = torch.randn(B, 2, H, W, device="cuda") * 2
+        wa = (B, C, H, W, H, W, float(W - 1), float(H - 1), 0, 0, 0, 1)
+        r = {"shape": "%dx%dx%dx%d" % (B, C, H, W)}
+        r["arf_corr_fwd_us"] = time_eager(lambda: lib.arf_corr_fwd(f1.data_ptr(), f2.data_ptr(), out.data_ptr(), B, C, H, W, 4, 1, 4, 1, 1, cs()))[0] * 1e6
+        r["arf_corr_bwd_us"] = time_eager(lambda: lib.arf_corr_bwd(f1.data_ptr(), f2.data_ptr(), go.data_ptr(), g1.data_ptr(), g2.data_ptr(), B, C, H, W, 4, 1, 4, 1, 1, cs()))[0] * 1e6
+        if ref is not None:
+            def rf():
+                rb1, rb2, o = f1.new_empty(0), f1.new_empty(0), f1.new_empty(0)
+                ref.forward(f1, f2, rb1, rb2, o, 4, 1, 4, 1, 1, 1)
+
+            def rb():
+                rb1, rb2, a, b = f1.new_empty(0), f1.new_empty(0), f1.new_empty(0), f1.new_empty(0)
+                ref.backward(f1, f2, rb1, rb2, go, a, b, 4, 1, 4, 1, 1, 1)
+            r["ref_cuda_corr_fwd_us"] = time_eager(rf)[0] * 1e6
+            r["ref_cuda_corr_bwd_us"] = time_eager(rb)[0] * 1e6
+        if B * C * H * W * 81 * 4 < 12e9:
+            r["aten_native_corr_fwd_us"] = time_eager(lambda: native_cost_volume(f1, f2), reps=5)[0] * 1e6
+            a1, a2 = f1.clone().requires_grad_(True), f2.clone().requires_grad_(True)
+
+            def nb():
+                o = native_cost_volume(a1, a2)
+                torch.autograd.grad(o, [a1, a2], go)
+            r["aten_native_corr_fwd_bwd_us"] = time_eager(nb, reps=5)[0] * 1e6
+        y = torch.empty_like(f1)
+        gx, gf = torch.empty_like(f1), torch.empty_like(fl)
+        r["arf_warp_fwd_us"] = time_eager(lambda: lib.arf_warp_fwd(f1.data_ptr(), fl.data_ptr(), y.data_ptr(), *wa, cs()))[0] * 1e6
+        r["arf_warp_bwd_us"] = time_eager(lambda: lib.arf_warp_bwd(f1.data_ptr(), fl.data_ptr(), f2.data_ptr(), gx.data_ptr(), gf.data_ptr(), *wa, cs()))[0] * 1e6
+        r["aten_grid_sample_fwd_us"] = time_eager(lambda: grid_sample_warp(f1, fl))[0] * 1e6
+        b1, bf = f1.clone().requires_grad_(True), fl.clone().requires_grad_(True)
+
+        def gb():
+            o = grid_sample_warp(b1, bf)
+            torch.autograd.grad(o, [b1, bf], f2)
+        r["aten_grid_sample_fwd_bwd_us"] = time_eager(gb)[0] * 1e6
+        rows_out.append(r)
+        print(json.dumps(r), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
@@ -290,6 +393,21 @@ def main():
             return lambda: lib.arf_image_pair_pack(dst.data_ptr(), src.data_ptr(), N // 2, Hi * Wi, 3, 8, 2.0, -1.0, cs())
         by = N * Hi * Wi * (3 + 8) * 4
         report("pair_pack", (N // 2, 6, Hi, Wi), by, 0, *time_graph(mk_pair, by))
+    if args.what == "compare":
+        crow = []
+        comparators(shapes if args.shapes else [(8, 32, 96, 128), (16, 32, 96, 128), (64, 32, 96, 128), (16, 64, 48, 64),
+                                                (16, 96, 24, 32), (16, 128, 12, 16), (1, 192, 6, 10), (1, 32, 96, 160)], crow)
+        if args.csv:
+            os.makedirs(os.path.dirname(args.csv), exist_ok=True)
+            keys = sorted({k for r in crow for k in r if k != "shape"})
+            with open(args.csv, "w") as f:
+                f.write("shape," + ",".join(keys) + ",vs_ref_cuda_fwd,vs_ref_cuda_bwd,vs_aten_native_fwd,vs_grid_sample_fwd\n")
+                for r in crow:
+                    q = lambda a, b: ("%.1f" % (r[a] / r[b])) if a in r and b in r else ""
+                    f.write(r["shape"] + "," + ",".join("%.1f" % r[k] if k in r else "" for k in keys) + "," +
+                            ",".join([q("ref_cuda_corr_fwd_us", "arf_corr_fwd_us"), q("ref_cuda_corr_bwd_us", "arf_corr_bwd_us"),
+                                      q("aten_native_corr_fwd_us", "arf_corr_fwd_us"), q("aten_grid_sample_fwd_us", "arf_warp_fwd_us")]) + "\n")
+        return
     if args.csv:
         os.makedirs(os.path.dirname(args.csv), exist_ok=True)
         with open(args.csv, "w") as f:
