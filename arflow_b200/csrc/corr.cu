@@ -562,6 +562,7 @@ inline bool is_fast(const CorrGeom& g, bool bwd) {
 
 extern thread_local int g_warp_variant;   // warp.cu
 extern thread_local int g_trisolve_variant;   // stencil.cu
+extern thread_local int g_census_variant;     // census.cu
 
 extern "C" int arf_debug_set(int key, int value) {
     if (key == 0) { g_force_no_tma = value; return ARF_OK; }
@@ -569,6 +570,7 @@ extern "C" int arf_debug_set(int key, int value) {
     if (key == 2) { g_probe = value; return ARF_OK; }
     if (key == 3) { g_warp_variant = value; return ARF_OK; }
     if (key == 4) { g_trisolve_variant = value; return ARF_OK; }
+    if (key == 5) { g_census_variant = value; return ARF_OK; }
     return ARF_EINVAL;
 }
 

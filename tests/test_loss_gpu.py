@@ -75,6 +75,52 @@ def test_census_golden():
     assert_close(ham, g["nopen_out0_f64"], RTOL_VALUE)
 
 
+@pytest.mark.parametrize("strip", [8, 16, 24])
+def test_census_pair_symmetric_kernels(strip):
+    """The pair-symmetric strip kernels (every unordered pixel pair evaluated once) against the golden fixture and,
+    on ragged shapes, against the per-pixel kernels: Hamming map, fused loss and both image gradients."""
+    from arflow_b200 import _lib
+    from arflow_b200 import loss_blocks as lb
+    from arflow_b200 import uflow_utils as uu
+    lib = _lib.load()
+    try:
+        lib.arf_debug_set(5, strip)
+        g = load_golden("census")
+        a, b, m = g["in0"], g["in1"], g["in2"]
+        (loss,), (ga, gb) = _grads(lambda x, y, mm: uu.census_loss(x, y, mm), [a, b, m], (0, 1))
+        assert_close(loss, g["loss_out0_f64"], RTOL_VALUE, "census_loss")
+        assert_close(ga, g["loss_grad0_f64"], RTOL_GRAD, "d census_loss / d image_a")
+        assert_close(gb, g["loss_grad1_f64"], RTOL_GRAD, "d census_loss / d image_b")
+        (h, w), (ga, gb) = _grads(lambda x, y, mm: uu.census_loss_no_penalty(x, y, mm), [a, b, m], (0, 1))
+        assert_close(h, g["nopen_out0_f64"], RTOL_VALUE, "hamming")
+        assert_close(ga, g["nopen_grad0_f64"], RTOL_GRAD)
+        assert_close(gb, g["nopen_grad1_f64"], RTOL_GRAD)
+        (d,), (gb,) = _grads(lambda x, y: lb.TernaryLoss(x, y, max_distance=1)[0], [a, b], (1,))
+        assert_close(d, g["tern1_out0_f64"], RTOL_VALUE)
+        assert_close(gb, g["tern1_grad1_f64"], RTOL_GRAD)
+        gen = torch.Generator().manual_seed(5)
+        for (B, H, W) in [(2, 37, 71), (1, 16, 32), (3, 100, 130), (1, 9, 200), (2, 64, 58), (1, 65, 59)]:
+            for md in (1, 2, 3):
+                x, y = torch.rand(B, 3, H, W, generator=gen), torch.rand(B, 3, H, W, generator=gen)
+                mm = (torch.rand(B, 1, H, W, generator=gen) > 0.3).float()
+                res = {}
+                for variant in (1, strip):
+                    lib.arf_debug_set(5, variant)
+                    if md == 3:
+                        fn = lambda p, r, k: uu.census_loss(p, r, k)
+                        res[variant] = _grads(fn, [x, y, mm], (0, 1))
+                    else:
+                        fn = lambda p, r: lb.TernaryLoss(p, r, max_distance=md)[0]
+                        res[variant] = _grads(fn, [x, y], (0, 1))
+                (o_ref,), g_ref = res[1]
+                (o_sym,), g_sym = res[strip]
+                assert_close(o_sym, o_ref.cpu(), RTOL_VALUE, "value %s md %d" % ((B, H, W), md))
+                for u, v in zip(g_sym, g_ref):
+                    assert_close(u, v.cpu(), RTOL_GRAD, "grad %s md %d" % ((B, H, W), md))
+    finally:
+        lib.arf_debug_set(5, 0)
+
+
 def test_smooth_blocks_golden():
     from arflow_b200 import loss_blocks as lb
     g = load_golden("smooth_blocks")

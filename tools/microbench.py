@@ -163,10 +163,11 @@ def main():
     ap.add_argument("--shapes", default=None, help="comma list of BxCxHxW")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (debug hook 1)")
     ap.add_argument("--probe", type=int, default=0, help="corr fwd probe mode (debug hook 2)")
-    ap.add_argument("--flow", default="both", choices=["iid", "smooth", "both"],
+    ap.add_argument("--flow", default="both", choices=["iid", "smooth", "wild", "both"],
                     help="warp flow field: iid N(0,2^2) px per pixel (config 5, worst case for gathers) or a smooth field "
                          "(1/8-resolution N(0,2^2) noise, bilinearly upsampled: what a flow network produces)")
     ap.add_argument("--warp-variant", type=int, default=0, help="debug hook 3: 1 = force direct warp kernels, 2 = force window kernels")
+    ap.add_argument("--census-variant", type=int, default=0, help="debug hook 5: 1 = per-pixel census kernels, 8..64 = strip height of the pair-symmetric ones")
     args = ap.parse_args()
     from arflow_b200 import _lib
     from arflow_b200.correlation import corr_out_dims
@@ -174,6 +175,7 @@ def main():
     lib.arf_debug_set(1, args.variant)
     lib.arf_debug_set(2, args.probe)
     lib.arf_debug_set(3, args.warp_variant)
+    lib.arf_debug_set(5, args.census_variant)
     hbm, src = peaks()
     rows = []
 
@@ -222,7 +224,12 @@ def main():
                 def mk(kind):
                     def make():
                         x = torch.randn(B, C, H, W, device="cuda")
-                        if flow_kind == "iid" or H < 16 or W < 16:
+                        if flow_kind == "wild":
+                            # what a random-init network produces on noise images (the bench's in-situ fields): 1/4-resolution
+                            # noise of tens of pixels, bilinearly upsampled - neighbouring pixels sample far-apart places
+                            fl = torch.nn.functional.interpolate(torch.randn(B, 2, max(H // 4, 1), max(W // 4, 1), device="cuda") * 40,
+                                                                 size=(H, W), mode="bilinear").contiguous()
+                        elif flow_kind == "iid" or H < 16 or W < 16:
                             fl = torch.randn(B, 2, H, W, device="cuda") * 2
                         else:
                             fl = torch.nn.functional.interpolate(torch.randn(B, 2, H // 8, W // 8, device="cuda") * 2,
@@ -237,7 +244,7 @@ def main():
                                                             gf.data_ptr(), *a, cs())
                         return lambda: lib.arf_warp_bwd(x.data_ptr(), fl.data_ptr(), gy.data_ptr(), None, gf.data_ptr(), *a, cs())
                     return make
-                tag = "" if flow_kind == "iid" else "_smooth"
+                tag = {"iid": "", "smooth": "_smooth", "wild": "_wild"}[flow_kind]
                 report("warp_fwd" + tag, (B, C, H, W), px * (8 * C + 8), px * C * 8, *time_graph(mk("fwd"), px * (8 * C + 8)))
                 report("warp_bwd" + tag, (B, C, H, W), px * (12 * C + 16), px * C * 16, *time_graph(mk("bwd"), px * (12 * C + 16)))
                 report("warp_bwdF" + tag, (B, C, H, W), px * (8 * C + 16), px * C * 16, *time_graph(mk("bwdF"), px * (8 * C + 16)))

@@ -41,7 +41,12 @@ def main():
             emit("%-70s %s %s" % (k, v[h.index(k)], units[h.index(k)]))
     src = list(csv.reader(io.StringIO(run([rep, "--page", "source", "--csv"]))))
     hdr = next(i for i, r in enumerate(src) if r and r[0] == "Address")
-    hh, data = src[hdr], [r for r in src[hdr + 1:] if len(r) == len(src[hdr])]
+    hh, data = src[hdr], []
+    for r in src[hdr + 1:]:        # one launch only: stop at the next launch's header block
+        if r and r[0] in ("Address", "Kernel Name"):
+            break
+        if len(r) == len(hh):
+            data.append(r)
     si, ie = hh.index("# Samples"), hh.index("Instructions Executed")
     stalls = [i for i, x in enumerate(hh) if x.startswith("stall_") and "Not Issued" not in x]
     tot = sum(int(r[si] or 0) for r in data) or 1
