@@ -13,6 +13,7 @@
 // Backward is a gather (no atomics): the gradient of gray pixel q collects, for every offset k, the term
 // of pixel q itself (q is the centre) and the term of pixel q-k (q is the neighbour).
 #include "common.cuh"
+#include <math.h>
 
 thread_local int g_census_variant = 0;   // test hook, per calling thread (arf_debug_set key 5): 1 = force the per-pixel kernels, 8..64 = strip height
 
@@ -636,14 +637,30 @@ census_bwd_sym(const float* __restrict__ im_a, const float* __restrict__ im_b, c
     }
 }
 
-// strip height: tall strips waste fewer rows (Hs + R evaluated per Hs owned) but give fewer warps; take the tallest
-// that still puts about eight warps on every SM
-inline int sym_strip_height(int B, int H, int W, int own_cols, int max_hs) {
-    if (g_census_variant >= 8 && g_census_variant <= 64) return g_census_variant < max_hs ? g_census_variant : max_hs;
-    const long long nsx = arf_cdiv(W, own_cols);
-    for (int hs = max_hs; hs > 16; hs -= 8)
-        if (nsx * arf_cdiv(H, hs) * B >= 8LL * ARF_NUM_SMS) return hs;
-    return H < 16 ? (H < 8 ? 8 : H) : 16;
+// Strip height: a strip evaluates Hs + R site rows for Hs owned ones, so tall strips waste less, but every strip is one
+// warp.  Measured on B200 (8x3x384x512 and 16x3x320x1024, Hs 8..64): an SM retires about 4.2 * (1 - exp(-w/4)) site
+// rows per microsecond with w resident warps, and a launch that fits in one wave lasts as long as its busiest SM.
+// Pick the height that minimises that estimate.
+inline int sym_strip_height(int B, int H, int W, int own_cols, int R, int resident_ctas) {
+    if (g_census_variant >= 8 && g_census_variant <= 64) return g_census_variant;
+    const long long nsx = arf_cdiv(W, own_cols), sms = ARF_NUM_SMS;
+    int best = 16;
+    double best_t = -1.0;
+    for (int hs = 8; hs <= 64; hs += 4) {
+        const long long nblk = (nsx * arf_cdiv(H, hs) * B + kSymWarps - 1) / kSymWarps;
+        double rows, w;
+        if (nblk <= sms * resident_ctas) {
+            const long long q = (nblk + sms - 1) / sms;
+            rows = (double)q * kSymWarps * (hs + R);
+            w = (double)q * kSymWarps;
+        } else {
+            rows = (double)nblk * kSymWarps * (hs + R) / (double)sms;
+            w = (double)resident_ctas * kSymWarps;
+        }
+        const double t = rows / (1.0 - exp(-w / 4.0));
+        if (best_t < 0 || t < best_t) { best = hs; best_t = t; }
+    }
+    return best;
 }
 
 }  // namespace
@@ -667,7 +684,7 @@ inline bool use_sym(int B, int H, int W) {
 template <int R>
 int launch_fwd_sym(const float* im_a, const float* im_b, const float* mask, float* hamming, float* partials, float* sums,
                    int B, int H, int W, float scale, float eps, float q, cudaStream_t st) {
-    const int hs = sym_strip_height(B, H, W, SymGeo<R>::kOwn, 64);
+    const int hs = sym_strip_height(B, H, W, SymGeo<R>::kOwn, R, 4);
     const int nsx = arf_cdiv(W, SymGeo<R>::kOwn), nsy = arf_cdiv(H, hs);
     const long long nstrips = (long long)nsx * nsy * B;
     const long long nblk = (nstrips + kSymWarps - 1) / kSymWarps;
@@ -685,7 +702,7 @@ template <int R>
 int launch_bwd_sym(const float* im_a, const float* im_b, const float* ghamming, const float* hamming, const float* mask,
                    const float* sums, const float* gloss, float* g_a, float* g_b, int B, int H, int W, float scale,
                    float eps, float q, cudaStream_t st) {
-    const int hs = sym_strip_height(B, H, W, SymGeo<R>::kOwn, 64);
+    const int hs = sym_strip_height(B, H, W, SymGeo<R>::kOwn, R, 3);
     const int nsx = arf_cdiv(W, SymGeo<R>::kOwn), nsy = arf_cdiv(H, hs);
     const long long nstrips = (long long)nsx * nsy * B;
     const long long nblk = (nstrips + kSymWarps - 1) / kSymWarps;

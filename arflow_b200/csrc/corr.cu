@@ -317,49 +317,57 @@ corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ C
 // ------------------------------------------------------------------ tiled backward, md=4 -
 // g1[c,y,x] = 1/C sum_{dy,dx} gO[(dy,dx),y,x]       * f2[c,y+dy,x+dx]           (kSecond = false, F = f2)
 // g2[c,y,x] = 1/C sum_{dy,dx} gO[(dy,dx),y-dy,x-dx] * f1[c,y-dy,x-dx]           (kSecond = true,  F = f1)
-// Both are gathers (no atomics, nothing to zero-fill).  Work item = (32 x 16 pixel tile, 32 channels).
-// 8 consumer warps = 2 row groups (8 rows each) x 4 channel groups (8 channels each); lane <-> x.
-// For each of the 9 horizontal displacements a warp pulls the 8 rows x 9 vertical displacements of gO
-// for its column into registers (from a TMA-streamed "slab" = the 9 planes of that dx) and reuses them
-// for its 8 channels: per channel 16 LDS (halo column of F) feed 72 FFMA into 8 accumulators.
-constexpr int kBTH = 16;                 // tile height of the backward
-constexpr int kBHH = kBTH + 2 * kMD;     // 24
-constexpr int kBC = 32;                  // channels per work item
+// Both are gathers (no atomics, nothing to zero-fill) and run in ONE launch: blockIdx.y selects the gradient.
+// Work item = (32 x 8*RG pixel tile, 8*CG channels); RG*CG consumer warps = RG row groups (8 rows each) x CG channel
+// groups (8 channels each); lane <-> x.  For each of the 9 horizontal displacements a warp pulls the 8 rows x 9
+// vertical displacements of gO for its column into registers (from a TMA-streamed "slab" = the 9 planes of that dx)
+// and reuses them for its 8 channels: per channel 16 LDS (halo column of F) feed 72 FFMA into 8 accumulators.
+// Item shapes in use (arf_corr_bwd picks by rounds x round time): <2,4> = 32x16 px x 32 channels, 8 consumer warps, one
+// CTA per SM, for problems that fill the machine with such items; <2,2> (16 channels) and <1,4> (32x8 px) for the coarse
+// pyramid levels, where two launches of the big item left most SMs idle behind a fixed ~35 us (16x32x24x32: 36 -> 13 us).
 constexpr int kBCg = 8;                  // channels per warp
-constexpr int kBStages = 3;              // slab ring depth
-constexpr int kBConsumers = 2 * (kBC / kBCg);          // 8 warps
-constexpr int kBwdThreads = 32 * (kBConsumers + 1);    // + producer warp
-constexpr int kNFBar = kBC / kBCg;                     // one "F arrived" barrier per channel group
 
-template <bool kSecond>
+template <int RG, int CG, int STG>
+struct BwdCfg {
+    static constexpr int kTileH = kTH * RG;           // tile height
+    static constexpr int kHaloH = kTileH + 2 * kMD;
+    static constexpr int kC = kBCg * CG;              // channels per work item
+    static constexpr int kConsumers = RG * CG;
+    static constexpr int kThreads = 32 * (kConsumers + 1);   // + producer warp
+    static constexpr int kStages = STG;               // slab ring depth
+};
+
+template <bool kSecond, int RG, int CG, int STG>
 struct BwdSmem {
+    using Cfg = BwdCfg<RG, CG, STG>;
     // The second gradient reads gO at (y-dy, x-dx): its slab carries the 4-px halo in both directions.
     // (A tiled TMA load needs a 16-byte aligned innermost coordinate — measured: x0-3 raises "illegal
     // instruction" — so the horizontal shift is applied when reading, not when loading.)
-    static constexpr int kSlabRows = kSecond ? kBHH : kBTH;
+    static constexpr int kSlabRows = kSecond ? Cfg::kHaloH : Cfg::kTileH;
     static constexpr int kSlabW = kSecond ? kHW : kTW;
-    float F[kBC][kBHH][kHW];                    // 122 880 B : halo tile of the other feature map
-    float slab[kBStages][kD][kSlabRows][kSlabW];  // 3 x 18 432 B (first) / 3 x 34 560 B (second)
-    uint64_t f_full[kNFBar], f_empty, s_full[kBStages], s_empty[kBStages];
+    float F[Cfg::kC][Cfg::kHaloH][kHW];                 // halo tile of the other feature map
+    float slab[STG][kD][kSlabRows][kSlabW];
+    uint64_t f_full[CG], f_empty, s_full[STG], s_empty[STG];
 };
 
-template <bool kSecond, bool kTma>
-__global__ void __launch_bounds__(kBwdThreads, 1)
-corr_bwd_md4(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapG,
-             const float* __restrict__ Fsrc, const float* __restrict__ gout, float* __restrict__ gin,
-             int B, int C, int H, int W, int tiles_x, int tiles_y, int nsuper, float inv_c) {
-    using Smem = BwdSmem<kSecond>;
+template <bool kSecond, bool kTma, int RG, int CG, int STG>
+__device__ __forceinline__ void corr_bwd_body(unsigned char* smem_raw, const CUtensorMap* mapF, const CUtensorMap* mapG,
+                                              const float* __restrict__ Fsrc, const float* __restrict__ gout,
+                                              float* __restrict__ gin, int B, int C, int H, int W, int tiles_x,
+                                              int tiles_y, int nsuper, float inv_c) {
+    using Cfg = BwdCfg<RG, CG, STG>;
+    using Smem = BwdSmem<kSecond, RG, CG, STG>;
     constexpr int kSlabRows = Smem::kSlabRows;
     constexpr int kSlabW = Smem::kSlabW;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int kBTH = Cfg::kTileH, kBHH = Cfg::kHaloH, kBC = Cfg::kC, kBConsumers = Cfg::kConsumers;
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kNFBar; ++i) arf::mbar_init(&sm.f_full[i], kTma ? 1 : 32);
+        for (int i = 0; i < CG; ++i) arf::mbar_init(&sm.f_full[i], kTma ? 1 : 32);
         arf::mbar_init(&sm.f_empty, kBConsumers);
-        for (int s = 0; s < kBStages; ++s) {
+        for (int s = 0; s < STG; ++s) {
             arf::mbar_init(&sm.s_full[s], kTma ? 1 : 32);
             arf::mbar_init(&sm.s_empty[s], kBConsumers);
         }
@@ -373,8 +381,8 @@ corr_bwd_md4(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ C
     if (warp == kBConsumers) {
         // ------------------------------------------------------------ producer warp
         if (kTma && lane == 0) {
-            arf::tma_prefetch_desc(&mapF);
-            arf::tma_prefetch_desc(&mapG);
+            arf::tma_prefetch_desc(mapF);
+            arf::tma_prefetch_desc(mapG);
         }
         uint32_t it = 0, item = 0;
         for (long long t = blockIdx.x; t < nitems; t += gridDim.x, ++item) {
@@ -385,15 +393,15 @@ corr_bwd_md4(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ C
             arf::mbar_wait(&sm.f_empty, (item & 1) ^ 1);
             if (kTma) {
                 if (lane == 0) {
-                    for (int gch = 0; gch < kNFBar; ++gch) {
+                    for (int gch = 0; gch < CG; ++gch) {
                         arf::mbar_arrive_expect_tx(&sm.f_full[gch], kBCg * kBHH * kHW * 4);
-                        arf::tma_load_4d(&sm.F[gch * kBCg][0][0], &mapF, &sm.f_full[gch], x0 - kMD, y0 - kMD,
+                        arf::tma_load_4d(&sm.F[gch * kBCg][0][0], mapF, &sm.f_full[gch], x0 - kMD, y0 - kMD,
                                          c0 + gch * kBCg, b);
                     }
                 }
             } else {
                 const float* fb = Fsrc + (size_t)b * C * plane;
-                for (int gch = 0; gch < kNFBar; ++gch) {
+                for (int gch = 0; gch < CG; ++gch) {
                     for (int e = lane; e < kBCg * kBHH * kHW; e += 32) {
                         int xx = e % kHW, rr = (e / kHW) % kBHH, cc = gch * kBCg + e / (kHW * kBHH);
                         int gx = x0 + xx - kMD, gy = y0 + rr - kMD, gc = c0 + cc;
@@ -404,15 +412,15 @@ corr_bwd_md4(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ C
                 }
             }
             for (int dx = 0; dx < kD; ++dx, ++it) {
-                const int s = it % kBStages;
-                arf::mbar_wait(&sm.s_empty[s], ((it / kBStages) & 1) ^ 1);
+                const int s = it % STG;
+                arf::mbar_wait(&sm.s_empty[s], ((it / STG) & 1) ^ 1);
                 // first: the tile itself; second: the tile with its 4-px halo
                 const int sx = kSecond ? x0 - kMD : x0;
                 const int sy = kSecond ? y0 - kMD : y0;
                 if (kTma) {
                     if (lane == 0) {
                         arf::mbar_arrive_expect_tx(&sm.s_full[s], kD * kSlabRows * kSlabW * 4);
-                        arf::tma_load_5d(&sm.slab[s][0][0][0], &mapG, &sm.s_full[s], sx, sy, dx, 0, b);
+                        arf::tma_load_5d(&sm.slab[s][0][0][0], mapG, &sm.s_full[s], sx, sy, dx, 0, b);
                     }
                 } else {
                     const float* gb = gout + (size_t)b * kD * kD * plane;
@@ -431,8 +439,8 @@ corr_bwd_md4(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ C
     }
 
     // ---------------------------------------------------------------- consumer warps
-    const int rg = warp / kNFBar;        // row group: rows rg*8 .. rg*8+7 of the tile
-    const int cgp = warp % kNFBar;       // channel group: channels cgp*8 .. cgp*8+7 of the work item
+    const int rg = warp / CG;        // row group: rows rg*8 .. rg*8+7 of the tile
+    const int cgp = warp % CG;       // channel group: channels cgp*8 .. cgp*8+7 of the work item
     const int r0 = rg * kTH;
     uint32_t it = 0, item = 0;
     for (long long t = blockIdx.x; t < nitems; t += gridDim.x, ++item) {
@@ -450,8 +458,8 @@ corr_bwd_md4(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ C
         arf::mbar_wait(&sm.f_full[cgp], item & 1);
 #pragma unroll 1
         for (int dx = 0; dx < kD; ++dx, ++it) {
-            const int s = it % kBStages;
-            arf::mbar_wait(&sm.s_full[s], (it / kBStages) & 1);
+            const int s = it % STG;
+            arf::mbar_wait(&sm.s_full[s], (it / STG) & 1);
             const int col = kSecond ? lane + 2 * kMD - dx : lane + dx;   // column in the halo frame
             float g[kTH][kD];
 #pragma unroll
@@ -492,30 +500,55 @@ corr_bwd_md4(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ C
     }
 }
 
-template <bool kSecond>
-int launch_bwd_md4(const float* Fsrc, const float* gout, float* gin, int B, int C, int H, int W, bool want_tma,
-                   cudaStream_t st) {
-    const int tiles_x = arf_cdiv(W, kTW), tiles_y = arf_cdiv(H, kBTH), nsuper = arf_cdiv(C, kBC);
+// maps: [0] f2 halo tiles, [1] gO tile slabs (first gradient); [2] f1 halo tiles, [3] gO halo slabs (second).
+struct BwdMaps { CUtensorMap m[4]; };
+
+// blockIdx.y + y_base: 0 = gradient w.r.t. f1, 1 = gradient w.r.t. f2
+template <bool kTma, int RG, int CG, int STG>
+__global__ void __launch_bounds__((BwdCfg<RG, CG, STG>::kThreads), 1)
+corr_bwd_md4(const __grid_constant__ BwdMaps maps, const float* __restrict__ f1, const float* __restrict__ f2,
+             const float* __restrict__ gout, float* __restrict__ g1, float* __restrict__ g2, int y_base, int B, int C,
+             int H, int W, int tiles_x, int tiles_y, int nsuper, float inv_c) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (blockIdx.y + y_base == 0)
+        corr_bwd_body<false, kTma, RG, CG, STG>(smem_raw, &maps.m[0], &maps.m[1], f2, gout, g1, B, C, H, W, tiles_x, tiles_y,
+                                                nsuper, inv_c);
+    else
+        corr_bwd_body<true, kTma, RG, CG, STG>(smem_raw, &maps.m[2], &maps.m[3], f1, gout, g2, B, C, H, W, tiles_x, tiles_y,
+                                               nsuper, inv_c);
+}
+
+template <int RG, int CG, int STG>
+int launch_bwd_md4(const float* f1, const float* f2, const float* gout, float* g1, float* g2, int B, int C, int H, int W,
+                   bool want_tma, int ctas_per_sm, cudaStream_t st) {
+    using Cfg = BwdCfg<RG, CG, STG>;
+    const int tiles_x = arf_cdiv(W, kTW), tiles_y = arf_cdiv(H, Cfg::kTileH), nsuper = arf_cdiv(C, Cfg::kC);
     const long long nitems = (long long)tiles_x * tiles_y * B * nsuper;
-    const int grid = (int)(nitems < ARF_NUM_SMS ? nitems : ARF_NUM_SMS);
-    constexpr int rows = BwdSmem<kSecond>::kSlabRows;
-    constexpr int cols = BwdSmem<kSecond>::kSlabW;
-    CUtensorMap mF, mG;
-    bool tma = want_tma && arf::tma_ok_nchw(Fsrc, W) && arf::tma_ok_nchw(gout, W) &&
-               arf::make_map_nchw(&mF, Fsrc, B, C, H, W, kHW, kBHH, kBCg) &&
-               arf::make_map_costvol(&mG, gout, B, kD, H, W, cols, rows);
+    const long long cap = (long long)ARF_NUM_SMS * ctas_per_sm;
+    const int ngrad = (g1 ? 1 : 0) + (g2 ? 1 : 0);
+    // both gradients share the machine: each gets half of the resident CTAs
+    const long long per = ngrad == 2 ? (cap + 1) / 2 : cap;
+    dim3 grid((unsigned)(nitems < per ? nitems : per), ngrad);
+    BwdMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    bool tma = want_tma && arf::tma_ok_nchw(f1, W) && arf::tma_ok_nchw(f2, W) && arf::tma_ok_nchw(gout, W);
+    if (tma && g1)
+        tma = arf::make_map_nchw(&maps.m[0], f2, B, C, H, W, kHW, Cfg::kHaloH, kBCg) &&
+              arf::make_map_costvol(&maps.m[1], gout, B, kD, H, W, kTW, Cfg::kTileH);
+    if (tma && g2)
+        tma = arf::make_map_nchw(&maps.m[2], f1, B, C, H, W, kHW, Cfg::kHaloH, kBCg) &&
+              arf::make_map_costvol(&maps.m[3], gout, B, kD, H, W, kHW, Cfg::kHaloH);
     const float inv_c = 1.0f / (float)C;
-    const size_t smem = sizeof(BwdSmem<kSecond>);
+    const size_t smem = g2 ? sizeof(BwdSmem<true, RG, CG, STG>) : sizeof(BwdSmem<false, RG, CG, STG>);
+    const int y_base = g1 ? 0 : 1;
     if (tma) {
-        ARF_ENSURE_SMEM((corr_bwd_md4<kSecond, true>), smem);
-        corr_bwd_md4<kSecond, true><<<grid, kBwdThreads, smem, st>>>(mF, mG, Fsrc, gout, gin, B, C, H, W, tiles_x,
-                                                                     tiles_y, nsuper, inv_c);
+        ARF_ENSURE_SMEM((corr_bwd_md4<true, RG, CG, STG>), sizeof(BwdSmem<true, RG, CG, STG>));
+        corr_bwd_md4<true, RG, CG, STG><<<grid, Cfg::kThreads, smem, st>>>(maps, f1, f2, gout, g1, g2, y_base, B, C, H, W,
+                                                                          tiles_x, tiles_y, nsuper, inv_c);
     } else {
-        ARF_ENSURE_SMEM((corr_bwd_md4<kSecond, false>), smem);
-        memset(&mF, 0, sizeof(mF));
-        memset(&mG, 0, sizeof(mG));
-        corr_bwd_md4<kSecond, false><<<grid, kBwdThreads, smem, st>>>(mF, mG, Fsrc, gout, gin, B, C, H, W, tiles_x,
-                                                                      tiles_y, nsuper, inv_c);
+        ARF_ENSURE_SMEM((corr_bwd_md4<false, RG, CG, STG>), sizeof(BwdSmem<true, RG, CG, STG>));
+        corr_bwd_md4<false, RG, CG, STG><<<grid, Cfg::kThreads, smem, st>>>(maps, f1, f2, gout, g1, g2, y_base, B, C, H, W,
+                                                                           tiles_x, tiles_y, nsuper, inv_c);
     }
     ARF_CHECK_LAUNCH();
     return ARF_OK;
@@ -640,15 +673,28 @@ extern "C" int arf_corr_bwd(const float* f1, const float* f2, const float* gout,
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (is_fast(g, true)) {
-        if (g1) {
-            rc = launch_bwd_md4<false>(f2, gout, g1, B, C, H, W, !g_force_no_tma, st);
-            if (rc) return rc;
+        if (!g1 && !g2) return ARF_OK;
+        // Three item shapes; a launch takes ceil(items / resident CTAs) rounds of roughly constant duration, so the shape
+        // is chosen by rounds x measured round time (B200, tools/microbench.py corr_bwd --variant 10|11|12, both gradients):
+        //   0: <2,4> 32x16 px x 32 ch, 1 CTA/SM, ~16 us    1: <2,2> 32x16 px x 16 ch, 1 CTA/SM, ~11 us
+        //   2: <1,4> 32x8 px x 32 ch, 2 CTAs/SM, ~22 us for a full pair
+        // e.g. 16x32x24x32: 18.5 / 13.1 / 12.9 us, 16x96x24x32: 33 / 33 / 26, 16x64x48x64: 50 / 62 / 64, 1x32x96x160: 18 / 13 / 14.
+        // (8-channel items, <2,1> and <1,1>, re-stream the gO slabs four times as often and lose everywhere: 65 / 68 us at
+        // 16x32x48x64 against 33.)
+        const int ngrad = (g1 ? 1 : 0) + (g2 ? 1 : 0);
+        const long long tx = arf_cdiv(W, kTW), sms = ARF_NUM_SMS;
+        const long long n0 = tx * arf_cdiv(H, 2 * kTH) * B * arf_cdiv(C, 32) * ngrad;
+        const long long n1 = tx * arf_cdiv(H, 2 * kTH) * B * arf_cdiv(C, 16) * ngrad;
+        const long long n2 = tx * arf_cdiv(H, kTH) * B * arf_cdiv(C, 32) * ngrad;
+        const long long c0 = ((n0 + sms - 1) / sms) * 16, c1 = ((n1 + sms - 1) / sms) * 11, c2 = ((n2 + 2 * sms - 1) / (2 * sms)) * 22;
+        int cfg = (c0 <= c1 && c0 <= c2) ? 0 : (c1 <= c2 ? 1 : 2);
+        if (g_variant >= 10 && g_variant <= 12) cfg = g_variant - 10;   // tuning hook
+        const bool tma = !g_force_no_tma;
+        switch (cfg) {
+            case 0: return launch_bwd_md4<2, 4, 3>(f1, f2, gout, g1, g2, B, C, H, W, tma, 1, st);
+            case 1: return launch_bwd_md4<2, 2, 2>(f1, f2, gout, g1, g2, B, C, H, W, tma, 1, st);
+            default: return launch_bwd_md4<1, 4, 3>(f1, f2, gout, g1, g2, B, C, H, W, tma, 2, st);
         }
-        if (g2) {
-            rc = launch_bwd_md4<true>(f1, gout, g2, B, C, H, W, !g_force_no_tma, st);
-            if (rc) return rc;
-        }
-        return ARF_OK;
     }
     long long total = (long long)B * C * H * W;
     if (g1) {
