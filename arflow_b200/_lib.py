@@ -70,6 +70,14 @@ PROTOTYPES = {
     "arf_ssim_fwd": [_P] * 4 + [ctypes.c_longlong] + [c_int] * 5 + [_P],
     "arf_ssim_bwd": [_P] * 7 + [ctypes.c_longlong] + [c_int] * 5 + [_P],
     "arf_resampler_fwd": [_P, _P, _P, ctypes.c_longlong, _P] + [c_int] * 4 + [ctypes.c_longlong, _P],
+    "arf_comm_flag_bytes": [],
+    "arf_comm_alloc": [ctypes.POINTER(c_void_p), c_size_t],
+    "arf_comm_free": [_P],
+    "arf_comm_ipc_get": [_P, ctypes.c_char_p],
+    "arf_comm_ipc_open": [ctypes.c_char_p, ctypes.POINTER(c_void_p)],
+    "arf_comm_ipc_close": [_P],
+    "arf_allreduce_f32": [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_int, c_int, c_size_t, c_size_t, c_float, c_int, _P],
+    "arf_comm_error": [_P, _P],
     "arf_resampler_bwd": [_P, _P, _P, ctypes.c_longlong, _P, _P, _P, _P, ctypes.c_longlong] + [c_int] * 4 + [ctypes.c_longlong, _P],
 }
 _RESTYPES = {"arf_error_string": ctypes.c_char_p, "arf_launch_count": ctypes.c_longlong,

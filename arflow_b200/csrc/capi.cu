@@ -27,6 +27,7 @@ extern "C" const char* arf_error_string(int code) {
         case ARF_EINVAL: return "invalid argument (shape, parameter or null pointer)";
         case ARF_EUNSUPPORTED: return "combination valid in the reference but not implemented";
         case ARF_EWORKSPACE: return "workspace too small";
+        case ARF_ETIMEOUT: return "a peer did not reach an all-reduce barrier in time";
         default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);

@@ -225,9 +225,9 @@ class _CensusHammingFunction(torch.autograd.Function):
 # the WHOLE batch (uflow_utils.py:293).  With a process group registered here, the per-rank denominator is replaced
 # by world * (global denominator) so that the gradient average over ranks equals the single-process gradient:
 #   mean_r [ W * num_r / (sum_r den_r + 1e-6) ] = sum_r num_r / (sum_r den_r + 1e-6).
-# The mask is detached, so this is a forward-only 4-byte all-reduce.  It is a collective inside the step, so it
-# cannot be used under CUDA-graph capture on this pool (see train_step.py); the default (None) keeps the per-rank
-# normaliser.
+# The mask is detached, so this is a forward-only 4-byte all-reduce.  It is a collective inside the step: through NCCL
+# it cannot be captured in a CUDA graph on this pool, through the peer-memory kernel (arflow_b200/comm.py) it can
+# (train_step.py).  The default (None) keeps the per-rank normaliser.
 _census_group = None
 
 
@@ -238,11 +238,19 @@ def set_census_normaliser_group(group, enabled=True):
 
 
 def globalise_census_sums(sums, group):
-    """sums = [num, den, num/(den+1e-6)] of this rank -> the same triple with the batch-global normaliser."""
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    den = sums[1:2].clone()
-    dist.all_reduce(den, group=group)
+    """sums = [num, den, num/(den+1e-6)] of this rank -> the same triple with the batch-global normaliser.
+    group: a torch.distributed process group, or an arflow_b200.comm.PeerAllReduce of >= 4 floats (capturable)."""
+    if hasattr(group, "all_reduce_"):
+        world = group.world
+        buf = group.buffer
+        buf[0:1].copy_(sums[1:2])
+        group.all_reduce_(0, 4, average=False)
+        den = buf[0:1].clone()
+    else:
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        den = sums[1:2].clone()
+        dist.all_reduce(den, group=group)
     out = sums.clone()
     out[1] = (den[0] + 1e-6) / world - 1e-6          # so that 1 / (out[1] + 1e-6) = world / (global den + 1e-6)
     out[2] = sums[0] / (out[1] + 1e-6)

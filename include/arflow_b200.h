@@ -42,6 +42,7 @@ extern "C" {
 #define ARF_EINVAL       -1   /* bad shape / parameter / null pointer */
 #define ARF_EUNSUPPORTED -2   /* valid in the reference but not implemented here */
 #define ARF_EWORKSPACE   -3   /* workspace too small */
+#define ARF_ETIMEOUT     -4   /* a peer did not reach an all-reduce barrier within ~2 s */
 
 /* padding modes of the warp (grid_sample padding_mode) */
 #define ARF_PAD_ZEROS      0
@@ -305,6 +306,28 @@ int arf_resampler_bwd(const float* data, const float* warp_x, const float* warp_
  * Cd must be 8 and C <= 8, else ARF_EUNSUPPORTED. */
 int arf_image_pair_pack(float* dst, const float* src, long long B, long long HW, int C, int Cd, float scale, float shift,
                         void* stream);
+
+/* ---------------------------------------------------------------- gradient all-reduce ---- */
+/* Data-parallel gradient exchange over NVLink peer memory (one process per GPU); replaces, for the benchmark driver,
+ * nn.DataParallel's gradient gather of the reference (trainer/base_trainer.py:75,131-147).
+ * arf_comm_alloc: cudaMalloc + zero fill of an IPC-exportable buffer (gradient storage, or a flag area of
+ * arf_comm_flag_bytes() bytes).  arf_comm_ipc_get / _open / _close: 64-byte CUDA IPC handle of such a buffer, and its
+ * mapping in a peer process (peer access is enabled on first use). */
+int arf_comm_flag_bytes(void);
+int arf_comm_alloc(void** ptr, size_t bytes);
+int arf_comm_free(void* ptr);
+int arf_comm_ipc_get(void* ptr, void* handle64);
+int arf_comm_ipc_open(const void* handle64, void** ptr);
+int arf_comm_ipc_close(void* ptr);
+/* In-place all-reduce of data[rank][offset .. offset+count) (floats; offset, count multiples of 4) across nranks <= 8
+ * processes: data[p] / flags[p] are rank p's gradient buffer and flag area as mapped in THIS process (host arrays of
+ * device pointers).  Result = scale * sum over ranks, bit-identical on every rank.  One kernel launch of `ctas` (<= 64)
+ * CTAs, no host synchronisation: capturable in a CUDA graph; every rank must issue the same sequence of calls with the
+ * same ctas. */
+int arf_allreduce_f32(float* const* data, unsigned* const* flags, int rank, int nranks, size_t offset, size_t count,
+                      float scale, int ctas, void* stream);
+/* Synchronises the stream; ARF_ETIMEOUT if a barrier of an earlier arf_allreduce_f32 on this flag area gave up. */
+int arf_comm_error(const unsigned* flags, void* stream);
 
 #ifdef __cplusplus
 }
