@@ -64,12 +64,14 @@ class PeerAllReduce:
             self.buffer = torch.as_tensor(self._holder, device=self.device)
         dist.barrier(group=self.group)     # every peer has mapped every buffer before the first kernel
 
-    def all_reduce_(self, start=0, end=None, average=True):
-        """In-place sum (or mean) of buffer[start:end] over the ranks; start and end multiples of 4."""
+    def all_reduce_(self, start=0, end=None, average=True, ctas=None):
+        """In-place sum (or mean) of buffer[start:end] over the ranks; start and end multiples of 4.  ctas: CTAs of this
+        launch (default: the constructor's) — few while other kernels should keep the SMs, up to 64 when nothing else
+        runs; every rank must pass the same value."""
         end = self.numel if end is None else int(end)
         scale = 1.0 / self.world if average else 1.0
         _lib.call("arf_allreduce_f32", self._peer_data, self._peer_flags, self.rank, self.world, int(start),
-                  end - int(start), scale, self.ctas, _lib.stream_ptr())
+                  end - int(start), scale, int(ctas or self.ctas), _lib.stream_ptr())
 
     def check(self):
         """Synchronise and raise if a barrier timed out (a peer never launched its kernel)."""

@@ -28,7 +28,7 @@ import torch.distributed as dist
 
 class UFlowTrainStep:
     def __init__(self, model, loss_fn, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, use_graph=True, world_size=1,
-                 n_buckets=3, global_census_norm=False, allreduce="auto", comm_ctas=24):
+                 n_buckets=4, global_census_norm=False, allreduce="auto", comm_ctas=16):
         dev0 = next(model.parameters()).device
         if allreduce == "auto":
             allreduce = "peer" if (world_size > 1 and dev0.type == "cuda") else "nccl"
@@ -100,7 +100,13 @@ class UFlowTrainStep:
         if world_size > 1:
             if self._on_cuda:
                 self._comm_stream = torch.cuda.Stream(device=dev)
-            bounds = [int(round(total * k / n_buckets)) for k in range(n_buckets + 1)]
+            # buckets in the order backward completes them (the flat buffer starts with the decoders and ends with the
+            # feature pyramid, whose gradients arrive last): the last bucket is small, because its all-reduce is the
+            # only one nothing is left to overlap with
+            fr = {1: [1.0], 2: [0.85, 1.0], 3: [0.5, 0.9, 1.0]}.get(n_buckets, None)
+            if fr is None:
+                fr = [0.9 * (k + 1) / (n_buckets - 1) for k in range(n_buckets - 1)] + [1.0]
+            bounds = [0] + [int(round(total * f)) for f in fr]
             starts = [s0 for (s0, _) in self._spans]
             snapped = [0] + [min(starts, key=lambda s0: abs(s0 - b)) for b in bounds[1:-1]] + [total]
             snapped = sorted(set(snapped))
@@ -149,7 +155,8 @@ class UFlowTrainStep:
 
     def _reduce_range(self, s, e):
         if self.allreduce_mode == "peer":
-            self._comm.all_reduce_(s, e, average=True)
+            # the range that ends the buffer is reduced after backward has finished: it may take the whole machine
+            self._comm.all_reduce_(s, e, average=True, ctas=64 if e >= self.flat_grad.numel() else None)
         elif self._on_cuda:
             dist.all_reduce(self.flat_grad[s:e], op=dist.ReduceOp.AVG)
         else:                            # gloo (CPU tests): no AVG op

@@ -71,7 +71,7 @@ def parse():
     ap.add_argument("--nchw", action="store_true", help="experiment: NCHW conv stacks (the default is channels-last)")
     ap.add_argument("--no-cudnn-benchmark", action="store_true",
                     help="disable cuDNN autotuning of the (out-of-scope) convolutions; about 11 % faster with it")
-    ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "fused"],
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "peer", "fused"],
                     help="gradient all-reduce of the multi-GPU step: the library's own NVLink kernel captured in the step "
                          "graph (fused), or NCCL between two graphs")
     ap.add_argument("--profile-step", action="store_true",
@@ -145,7 +145,7 @@ HOTPATH = ("arf_corr_fwd", "arf_corr_bwd", "arf_warp_fwd", "arf_warp_bwd", "arf_
            "arf_ssim_fwd", "arf_ssim_bwd", "arf_featnorm_fwd", "arf_featnorm_bwd", "arf_resize_bilinear_fwd",
            "arf_resize_bilinear_bwd", "arf_corr_level_fwd")
 CENSUS_MUFU_FWD = 1.5   # MUFU per pixel and offset: each unordered pixel pair is evaluated once (3 MUFU per pair)
-CENSUS_MUFU_BWD = 3.0   # the backward evaluates the pair term at both of its pixels (gather form)
+CENSUS_MUFU_BWD = 1.5   # same for the backward: one evaluation per unordered pair, +X to one end and -X to the other
 
 
 def alg_bytes(name, a):
@@ -507,9 +507,15 @@ def build_step(args, dev, world):
         model.train()
         loss_fn = UFlowLoss(types.SimpleNamespace(edge_constant=150, w_smooth=4.0, w_census=1.0, with_bk=True,
                                                    smooth_order=cfg["smooth_order"]))
+        # N > 1: the census loss keeps the reference's batch-global normaliser (uflow_utils.py:293) through a 16-byte
+        # peer all-reduce inside the captured step, so every N optimises the same loss as the single-process reference
         step = UFlowTrainStep(model, loss_fn, lr=1e-4, use_graph=not args.no_graph, world_size=world,
-                              allreduce=args.allreduce)
-        eager = lambda: UFlowTrainStep(model, loss_fn, lr=1e-4, use_graph=False, world_size=1)
+                              allreduce=args.allreduce, global_census_norm=(world > 1 and args.allreduce != "nccl"))
+        import copy
+        fresh = copy.deepcopy(model)      # in-situ kernel timings run on the initial weights, see main_b200
+
+        def eager():
+            return UFlowTrainStep(fresh, loss_fn, lr=1e-4, use_graph=False, world_size=1)
         return step, eager, B, 6, model
     if cid == 3:
         from arflow_b200.uflow_elbo_loss import UFlowElboLoss
@@ -797,8 +803,8 @@ def main_b200(args):
             roof["step_share"] = k["ms"] / n_prof / (ms_total / args.steps)
             roof["traffic_source"] = tsrc
             roof["note"] = ("dominant SURVEY-8(a) entry point of the step by device time; algorithmic bytes (flops) / CUDA-event "
-                            "time of the C-ABI call, in situ (L2-warm, inside an eager step; one C-ABI call may launch more than "
-                            "one kernel). bound = whichever of HBM bytes, FP32 flops, MUFU ops takes longest at the measured "
+                            "time of the C-ABI call, in situ (L2-warm, inside eager steps of a copy of the freshly initialised "
+                            "network; one C-ABI call may launch more than one kernel). bound = whichever of HBM bytes, FP32 flops, MUFU ops takes longest at the measured "
                             "peaks; all three fractions are given.")
         for name, k in kernels.items():
             k["us_per_step"] = 1e3 * k["ms"] / n_prof
