@@ -70,7 +70,7 @@ def parse():
     ap.add_argument("--no-hotpath", action="store_true", help="skip the isolated hot-path kernel timings")
     ap.add_argument("--nchw", action="store_true", help="experiment: NCHW conv stacks (the default is channels-last)")
     ap.add_argument("--no-cudnn-benchmark", action="store_true",
-                    help="disable cuDNN autotuning of the (out-of-scope) convolutions; about 11 % faster with it")
+                    help="disable cuDNN autotuning of the (out-of-scope) convolutions; about 11 %% faster with it")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "peer", "fused"],
                     help="gradient all-reduce of the multi-GPU step: the library's own NVLink kernel captured in the step "
                          "graph (fused), or NCCL between two graphs")
@@ -103,13 +103,17 @@ def measured_peaks(live=True):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms.  Started before the warm-up (nvidia-smi needs ~0.5 s to
+    print its first row); `mark()` opens the window at the start of the timed region and `stop()` closes it, so only rows
+    taken under the timed load are reported.  A region shorter than three samples is widened by the rows just before it
+    (the warm-up steps, same load)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.rows = []
         self.proc = None
+        self.first = 0
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -123,15 +127,21 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self):
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        rows = self.rows[self.first:]
+        if len(rows) < 3:
+            rows = self.rows[max(0, len(self.rows) - 3):]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].startswith("Active")})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].startswith("Active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -704,6 +714,7 @@ def main_b200(args):
         return
 
     # ---- warm-up (also captures the graph) ----
+    sampler = ClockSampler(local) if rank == 0 else None
     W_ = max(args.warmup, 3)
     for i in range(W_):
         out = step(devb[i % n_host])
@@ -711,9 +722,10 @@ def main_b200(args):
     launches_per_step = getattr(step, "launches_per_step", None)   # kernels of this library inside one graph replay
 
     # ---- timed region: inputs resident in HBM ----
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = _lib.launch_count()
     barrier()
+    if sampler:
+        sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -721,7 +733,6 @@ def main_b200(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if sampler else None
     eager_launches = _lib.launch_count() - l0
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -760,6 +771,7 @@ def main_b200(args):
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_s = float(t_e2e.item())
+    clocks = sampler.stop() if sampler else None     # window = timed region + end-to-end region (the same steps)
 
     # ---- in-situ kernel timings (eager, events around each C-ABI call), rank 0, single GPU ----
     kernels, roof, hot, pk = {}, None, None, None
