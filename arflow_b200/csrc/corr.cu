@@ -11,6 +11,9 @@
 //   at x+dx from shared memory (24 conflict-free LDS.32) and issues 72 FFMA.  f1/f2 never go
 //   through an NHWC staging copy (the reference's channels_first pass, .cu:15-39, is gone):
 //   tiles are staged straight from NCHW, zero padding is produced while staging.
+// Tiled forward, "pair-shared" layout (corr_fwd_md4_p2, the default wherever it fills the machine): 32 x 12 tiles, a
+//   warp covers a PAIR of horizontal displacements and the two lanes of a lane pair read the same 8 bytes of the f2
+//   halo row - one LDS.64 slot delivers two operands, and the register pair is the packed operand of FFMA2.
 #include "common.cuh"
 #include "tma.cuh"
 #include <string.h>
@@ -311,8 +314,162 @@ corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ C
 //   * 6 stages of 4 channels instead of 3 of 8: 153-157 us; two row groups per CTA (1 CTA/SM): slower;
 //   * the same FFMA2 packing in the backward kernels (40 FFMA2 per channel with zero-padded edge pairs, bit-identical):
 //     398 vs 345 us for both gradients - dropped.
-// Getting further needs fewer shared-memory operands per FMA than a 72-accumulator thread tile allows (bigger tiles
-// do not fit two CTAs per SM) or the tensor pipe, which cannot meet the 1e-5 parity bar.
+// Round 2: tools/lds_probe.cu shows what the loop is bound by - the LSU issues one warp-wide LDS.32 per ~1.45 cycles
+// (not 1.0), so 24 LDS.32 per 72 FMAs cap the FMA pipe at ~50 %; the kernel ran at 80 % of that cap.  Also measured:
+//   * one CTA per SM with ~170 registers and the next channel's 24 operands prefetched across stage and tile boundaries
+//     (explicit double buffering, 9 consumer warps): 154 us - latency was not the limit, the LDS slot count is;
+//   * corr_fwd_md4_p2 below (lane pairs share 64-bit operands): 127 us with 16 warps of 128 registers (R = 4 rows x
+//     3 row groups); 144 us with R = 6 x 2 (11 warps, 168 registers), 213 us with R = 8 x 1 (6 warps); its loop without
+//     the output stores 99 us; scalar FFMAs instead of FFMA2 165 us; starting the row groups one stage apart so that
+//     their epilogues do not coincide 140 us (worse: the groups then compete for the LSU instead of sharing L1 lines).
+
+// ------------------------------------------------------------------ tiled forward, pair-shared 64-bit operands ---
+// Measured on B200 (tools/lds_probe.cu): a warp-wide LDS.32 costs ~1.45 LSU cycles whatever its addresses, an LDS.64
+// whose lane pairs (2p, 2p+1) read the SAME 8 bytes costs ~1.48 - the same instruction slot delivers two operands.  The
+// kernels above are bound by exactly that slot (24 LDS.32 per 72 FMAs).  Here the two lanes of a pair share their f2
+// operand: lane l <-> pixel x = l as before, but a warp covers a PAIR of horizontal displacements.  With d' even and
+// xe = x & ~1, the 8 bytes at halo columns (xe + d', xe + d' + 1) are, for the even lane, its operands for dx = d' and
+// d' + 1, and for the odd lane (x = xe + 1) those for dx = d' - 1 and d'.  Five warps (d' = -4, -2, 0, 2, 4) cover the nine
+// displacements (dx = -5 / +5 of the outer warps are computed and dropped: 10 % waste).  The loaded register pair is
+// directly the packed operand of FFMA2 (accumulator pair = the lane's two displacements), f1 is the broadcast scalar.
+// Per channel and warp: R LDS.32 + (R + 8) LDS.64 feed 9R FFMA2 = 18R FMAs  (R = 6: 29 LSU cycles per 108 FMAs, the
+// kernels above: 35 per 72).
+template <int TH, int kCc>
+struct __align__(128) FwdStageP {
+    float s1[kCc][TH][kTW];
+    float s2[kCc][TH + 2 * kMD][kHW];
+};
+template <int TH, int kCc>
+constexpr size_t fwd_p2_smem(int stages) { return stages * sizeof(FwdStageP<TH, kCc>) + 2 * stages * sizeof(uint64_t); }
+
+__device__ __forceinline__ unsigned long long lds_pair(const float* p) {
+    unsigned long long v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(arf::smem_u32(p)));
+    return v;
+}
+
+constexpr int kPW = 5;   // displacement-pair warps per row group
+
+template <int R, int RG, int kStg>
+__global__ void __launch_bounds__(32 * (kPW * RG + 1), 1)
+corr_fwd_md4_p2(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
+                float* __restrict__ out, int B, int C, int H, int W, int tiles_x, int tiles_y, float inv_c, int probe) {
+    // probe (tuning only): 2 = skip the output stores
+    constexpr int kCc = 8;
+    constexpr int TH = R * RG;
+    constexpr int kConsumers = kPW * RG;
+    using Stage = FwdStageP<TH, kCc>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Stage* stg = reinterpret_cast<Stage*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStg * sizeof(Stage));
+    uint64_t* empty = full + kStg;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStg; ++s) {
+            arf::mbar_init(&full[s], 1);
+            arf::mbar_init(&empty[s], kConsumers);
+        }
+        arf::mbar_fence_init();
+    }
+    __syncthreads();
+    const int ntiles = tiles_x * tiles_y * B;
+    const int nchunks = (C + kCc - 1) / kCc;
+    const size_t plane = (size_t)H * W;
+
+    if (warp == kConsumers) {
+        if (lane == 0) {
+            arf::tma_prefetch_desc(&map1);
+            arf::tma_prefetch_desc(&map2);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+                const int x0 = tx * kTW, y0 = ty * TH;
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    arf::mbar_wait(&empty[s], ph ^ 1);
+                    arf::mbar_arrive_expect_tx(&full[s], (uint32_t)sizeof(Stage));
+                    arf::tma_load_4d(&stg[s].s1[0][0][0], &map1, &full[s], x0, y0, ch * kCc, b);
+                    arf::tma_load_4d(&stg[s].s2[0][0][0], &map2, &full[s], x0 - kMD, y0 - kMD, ch * kCc, b);
+                    if (++s == kStg) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+
+    const int rg = warp / kPW, wp = warp % kPW;
+    const int dpr = 2 * wp;                    // d' + 4
+    const int odd = lane & 1;
+    const int col = (lane & ~1) + dpr;         // halo column of the pair's first operand
+    const int r0 = rg * R;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+        const int x0 = tx * kTW, y0 = ty * TH + r0;
+        unsigned long long acc[R][kD];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int d = 0; d < kD; ++d) acc[r][d] = 0ull;
+#pragma unroll 1
+        for (int ch = 0; ch < nchunks; ++ch) {
+            arf::mbar_wait(&full[s], ph);
+            const float* s1c = &stg[s].s1[0][r0][lane];
+            const float* s2c = &stg[s].s2[0][r0][col];
+#pragma unroll
+            for (int cc = 0; cc < kCc; ++cc) {
+                float a[R];
+                unsigned long long bb[R + 2 * kMD];
+#pragma unroll
+                for (int r = 0; r < R; ++r) a[r] = s1c[(cc * TH + r) * kTW];
+#pragma unroll
+                for (int k = 0; k < R + 2 * kMD; ++k) bb[k] = lds_pair(s2c + (cc * (TH + 2 * kMD) + k) * kHW);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const unsigned long long ap = f2_pack(a[r], a[r]);
+#pragma unroll
+                    for (int d = 0; d < kD; ++d) f2_fma(acc[r][d], ap, bb[r + d]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) arf::mbar_arrive(&empty[s]);
+            if (++s == kStg) { s = 0; ph ^= 1; }
+        }
+        // epilogue.  Displacement plane dpr gets a full 128-byte row (even lanes: first accumulator, odd lanes: second);
+        // the other accumulator goes to plane dpr + 1 (even lanes) / dpr - 1 (odd lanes), whose other half comes from
+        // the neighbouring warp.
+        const int gx = x0 + lane;
+        if (probe == 2) {
+            float va, vb;
+            f2_unpack(acc[0][0], va, vb);
+            if (va == 123.456f) out[0] = vb;   // keep the work alive
+            continue;
+        }
+        if (gx < W) {
+            const int p2 = odd ? dpr - 1 : dpr + 1;
+            const bool ok2 = p2 >= 0 && p2 < kD;
+            float* o1 = out + ((size_t)b * (kD * kD) + dpr) * plane + (size_t)y0 * W + gx;
+            float* o2 = out + ((size_t)b * (kD * kD) + (ok2 ? p2 : dpr)) * plane + (size_t)y0 * W + gx;
+            const size_t dstride = (size_t)kD * plane;
+#pragma unroll
+            for (int d = 0; d < kD; ++d) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float va, vb;
+                    f2_unpack(acc[r][d], va, vb);
+                    if (y0 + r < H) {
+                        __stcs(o1 + r * W, (odd ? vb : va) * inv_c);
+                        if (ok2) __stcs(o2 + r * W, (odd ? va : vb) * inv_c);
+                    }
+                }
+                o1 += dstride;
+                o2 += dstride;
+            }
+        }
+    }
+}
 
 // ------------------------------------------------------------------ tiled backward, md=4 -
 // g1[c,y,x] = 1/C sum_{dy,dx} gO[(dy,dx),y,x]       * f2[c,y+dy,x+dx]           (kSecond = false, F = f2)
@@ -626,20 +783,46 @@ extern "C" int arf_corr_fwd(const float* f1, const float* f2, float* out, int B,
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (is_fast(g, false)) {
-        const int rg = (g_variant == 3 || g_variant == 4) ? 2 : 1;
-        const int tiles_x = arf_cdiv(W, kTW), tiles_y = arf_cdiv(H, kTH * rg);
-        const long long ntiles = (long long)tiles_x * tiles_y * B;
-        if (ntiles > 0x7fffffffLL) return ARF_EINVAL;
-        const int cc = kCcDefault;   // channels per stage
+        const int tiles_x = arf_cdiv(W, kTW);
+        const float inv_c = 1.0f / (float)C;
+        const bool tma = !g_force_no_tma && arf::tma_ok_nchw(f1, W) && arf::tma_ok_nchw(f2, W);
+        const long long sms = ARF_NUM_SMS;
+        // Two tiled kernels.  "p2" (pair-shared 64-bit operands, 32x12 tiles, one 16-warp CTA per SM) needs TMA and wins
+        // whenever its tile count fills the machine as well as the 32x8 tiles of the column-thread kernel (two CTAs per
+        // SM) do.  A launch lasts rounds x tile time; measured tile times per channel and tile row (B200, tools/
+        // microbench.py corr_fwd --variant 30 | 31): 0.0235 us (p2) against 0.0529 us with two CTAs sharing an SM.
+        // E.g. 64x32x96x128: 126 vs 149 us, 64x96x24x32: 26 vs 38, 8x64x56x128 (160 p2 tiles = 2 rounds): 35 vs 28.
+        const long long n_p2 = (long long)tiles_x * arf_cdiv(H, 12) * B, n_ct = (long long)tiles_x * arf_cdiv(H, kTH) * B;
+        if (n_ct > 0x7fffffffLL) return ARF_EINVAL;
+        const double t_p2 = (double)((n_p2 + sms - 1) / sms) * 12 * 0.0235;
+        const double t_ct = (double)((n_ct + 2 * sms - 1) / (2 * sms)) * kTH * 0.0529;
+        bool use_p2 = tma && t_p2 < 0.97 * t_ct;
+        if (g_variant == 30) use_p2 = tma;          // tuning hooks: force either kernel
+        if (g_variant == 31) use_p2 = false;
+        if (use_p2) {
+            constexpr int R = 4, RG = 3, STG = 4;
+            CUtensorMap m1, m2;
+            if (arf::make_map_nchw(&m1, f1, B, C, H, W, kTW, R * RG, 8) &&
+                arf::make_map_nchw(&m2, f2, B, C, H, W, kHW, R * RG + 2 * kMD, 8)) {
+                auto kern = corr_fwd_md4_p2<R, RG, STG>;
+                ARF_ENSURE_SMEM(kern, (fwd_p2_smem<R * RG, 8>(STG)));
+                const int tiles_y = arf_cdiv(H, R * RG);
+                const int grid = (int)(n_p2 < sms ? n_p2 : sms);
+                kern<<<grid, 32 * (kPW * RG + 1), fwd_p2_smem<R * RG, 8>(STG), st>>>(m1, m2, out, B, C, H, W, tiles_x,
+                                                                                     tiles_y, inv_c, g_probe);
+                ARF_CHECK_LAUNCH();
+                return ARF_OK;
+            }
+        }
+        const int tiles_y = arf_cdiv(H, kTH);
+        const long long ntiles = n_ct;
         CUtensorMap m1, m2;
-        bool tma = !g_force_no_tma && arf::tma_ok_nchw(f1, W) && arf::tma_ok_nchw(f2, W) &&
-                   arf::make_map_nchw(&m1, f1, B, C, H, W, kTW, kTH * rg, cc) &&
-                   arf::make_map_nchw(&m2, f2, B, C, H, W, kHW, kTH * rg + 2 * kMD, cc);
-        if (!tma) {
+        bool tma_ct = tma && arf::make_map_nchw(&m1, f1, B, C, H, W, kTW, kTH, kCcDefault) &&
+                      arf::make_map_nchw(&m2, f2, B, C, H, W, kHW, kTH + 2 * kMD, kCcDefault);
+        if (!tma_ct) {
             memset(&m1, 0, sizeof(m1));
             memset(&m2, 0, sizeof(m2));
         }
-        const float inv_c = 1.0f / (float)C;
 #define ARF_LAUNCH_FWD(TMA, RG, STG, MINB, UNR, F2, CC)                                                          \
     do {                                                                                                         \
         auto kern = corr_fwd_md4<TMA, RG, STG, MINB, UNR, F2, CC>;                                               \
@@ -648,9 +831,7 @@ extern "C" int arf_corr_fwd(const float* f1, const float* f2, float* out, int B,
         kern<<<grid, 32 * (kD * RG + 1), fwd_smem<RG, CC>(STG), st>>>(m1, m2, f1, f2, out, B, C, H, W, tiles_x,  \
                                                                       tiles_y, inv_c, g_probe);                  \
     } while (0)
-        if (!tma) ARF_LAUNCH_FWD(false, 1, 3, 2, 1, false, 8);
-        else if (g_variant == 3) ARF_LAUNCH_FWD(true, 2, 4, 1, 1, false, 8);
-        else if (g_variant == 4) ARF_LAUNCH_FWD(true, 2, 3, 1, 1, false, 8);
+        if (!tma_ct) ARF_LAUNCH_FWD(false, 1, 3, 2, 1, false, 8);
         else if (g_variant == 7) ARF_LAUNCH_FWD(true, 1, 3, 2, 1, false, 8);   // scalar FFMA loop (same bits)
         else ARF_LAUNCH_FWD(true, 1, 3, 2, 2, true, 8);                        // FFMA2 loop, two channels in flight
 #undef ARF_LAUNCH_FWD
