@@ -92,6 +92,72 @@ __global__ void corr_bwd_literal(const float* __restrict__ other, const float* _
     }
 }
 
+// ------------------------------------------------------------------ small problems, md = 4 geometry --------
+// The coarsest pyramid levels (PWC-Lite inference: 1 x 192 x 6 x 10, pwclite.py:113) have a few dozen pixels and a few
+// hundred channels: one thread per output element (the literal kernels) walks 81 x 2 or C x 2 dependent loads and takes
+// 13-33 us forward / ~100 us backward.  Here a WARP owns the output element and its lanes split the reduction
+// (channels forward, the 81 displacements backward), then a shuffle tree: a few microseconds.
+__global__ void __launch_bounds__(256)
+corr_fwd_small_md4(const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ out, int B, int C,
+                   int H, int W) {
+    const int lane = threadIdx.x & 31;
+    const long long nout = (long long)B * 81 * H * W;
+    const size_t plane = (size_t)H * W;
+    const float inv_c = 1.0f / (float)C;
+    for (long long o = blockIdx.x * 8LL + (threadIdx.x >> 5); o < nout; o += gridDim.x * 8LL) {
+        const int x = (int)(o % W);
+        long long t = o / W;
+        const int y = (int)(t % H); t /= H;
+        const int tc = (int)(t % 81), b = (int)(t / 81);
+        const int y2 = y + tc / 9 - 4, x2 = x + tc % 9 - 4;
+        float acc = 0.f;
+        if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) {
+            const float* p1 = f1 + (size_t)b * C * plane + (size_t)y * W + x;
+            const float* p2 = f2 + (size_t)b * C * plane + (size_t)y2 * W + x2;
+            for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(p1 + c * plane), __ldg(p2 + c * plane), acc);
+        }
+        acc = arf_warp_sum(acc);
+        if (lane == 0) out[o] = acc * inv_c;
+    }
+}
+
+// which (blockIdx.y + y_base) = 0: gradient w.r.t. f1, 1: gradient w.r.t. f2 (formulas at the tiled backward below)
+__global__ void __launch_bounds__(256)
+corr_bwd_small_md4(const float* __restrict__ f1, const float* __restrict__ f2, const float* __restrict__ gout,
+                   float* __restrict__ g1, float* __restrict__ g2, int y_base, int B, int C, int H, int W) {
+    const int lane = threadIdx.x & 31;
+    const int which = blockIdx.y + y_base;
+    const float* __restrict__ other = which ? f1 : f2;
+    float* __restrict__ gin = which ? g2 : g1;
+    const long long nel = (long long)B * C * H * W;
+    const size_t plane = (size_t)H * W;
+    const float inv_c = 1.0f / (float)C;
+    for (long long e = blockIdx.x * 8LL + (threadIdx.x >> 5); e < nel; e += gridDim.x * 8LL) {
+        const int x = (int)(e % W);
+        long long t = e / W;
+        const int y = (int)(t % H); t /= H;
+        const int c = (int)(t % C), b = (int)(t / C);
+        const float* ob = other + ((size_t)b * C + c) * plane;
+        const float* gb = gout + (size_t)b * 81 * plane;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int tc = lane + 32 * k;
+            if (tc < 81) {
+                const int dy = tc / 9 - 4, dx = tc % 9 - 4;
+                // first: gO at the pixel itself, f2 at the displaced pixel; second: both at the pixel displaced back
+                const int yo = which ? y - dy : y + dy, xo = which ? x - dx : x + dx;
+                if (yo >= 0 && yo < H && xo >= 0 && xo < W) {
+                    const size_t go_off = which ? (size_t)yo * W + xo : (size_t)y * W + x;
+                    acc = fmaf(__ldg(gb + tc * plane + go_off), __ldg(ob + (size_t)yo * W + xo), acc);
+                }
+            }
+        }
+        acc = arf_warp_sum(acc);
+        if (lane == 0) gin[e] = acc * inv_c;
+    }
+}
+
 // Packed FP32 FMA (FFMA2, sm_100): two IEEE fused multiply-adds per lane and instruction.  ptxas turns a pair
 // built from the same scalar into the broadcast operand form (R.F32), so no MOV is spent on packing.
 __device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
@@ -744,8 +810,8 @@ inline bool is_fast(const CorrGeom& g, bool bwd) {
     if (!is_md4(g) || g_variant == 5) return false;
     if (g_variant == 6) return true;
     const long long px = (long long)g.B * g.H * g.W;
-    if (bwd) return !(g.W % 4 != 0 && px <= 512);
-    return px > 1024;
+    if (bwd) return px > 128;       // below: corr_bwd_small_md4 (1x192x6x10: 10 us against 98 literal / 342 tiled)
+    return px > 1024;               // below: literal, or corr_fwd_small_md4 up to 128 pixels (1x192x6x10: 4 vs 13 us)
 }
 
 }  // namespace
@@ -837,6 +903,11 @@ extern "C" int arf_corr_fwd(const float* f1, const float* f2, float* out, int B,
 #undef ARF_LAUNCH_FWD
         ARF_CHECK_LAUNCH();
         return ARF_OK;
+    } else if (is_md4(g) && g_variant != 5 && (long long)B * H * W <= 128) {
+        // a few dozen pixels, hundreds of channels: a warp per output element (at 240+ pixels its strided channel
+        // loads lose to the literal kernel: 1x128x12x20 14 vs 12 us)
+        const long long nout = (long long)B * 81 * H * W;
+        corr_fwd_small_md4<<<arf_grid_1d(nout * 32, 256, 16), 256, 0, st>>>(f1, f2, out, B, C, H, W);
     } else {
         long long total = (long long)B * g.D * g.D * g.oH * g.oW;
         corr_fwd_literal<<<arf_grid_1d(total, 256), 256, 0, st>>>(f1, f2, out, g);
@@ -878,6 +949,13 @@ extern "C" int arf_corr_bwd(const float* f1, const float* f2, const float* gout,
         }
     }
     long long total = (long long)B * C * H * W;
+    if (is_md4(g) && g_variant != 5) {
+        if (!g1 && !g2) return ARF_OK;
+        dim3 grid(arf_grid_1d(total * 32, 256, 16), (g1 ? 1 : 0) + (g2 ? 1 : 0));
+        corr_bwd_small_md4<<<grid, 256, 0, st>>>(f1, f2, gout, g1, g2, g1 ? 0 : 1, B, C, H, W);
+        ARF_CHECK_LAUNCH();
+        return ARF_OK;
+    }
     if (g1) {
         corr_bwd_literal<<<arf_grid_1d(total, 256), 256, 0, st>>>(f2, gout, g1, g, 0);
         ARF_CHECK_LAUNCH();

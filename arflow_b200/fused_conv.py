@@ -101,8 +101,10 @@ class _ConvBiasLeaky(torch.autograd.Function):
 def conv_bias_leaky(conv, x, negative_slope, weight=None, bias=None, real_in=None):
     """leaky_relu(conv(x)) for an nn.Conv2d `conv` (groups 1); `weight` / `bias` override conv.weight / conv.bias
     (padded / channels-last copies).  real_in: number of leading input channels that are not zero padding (the
-    image's 3 of 8 in the first pyramid layer) - the weight gradient of the rest is returned as zero.  CUDA tensors take the fused path; a CPU tensor means the caller is the
-    oracle-backed CPU twin of the network (tests, bench.py's cpu_baseline) and gets plain torch."""
+    image's 3 of 8 in the first pyramid layer) - the weight gradient of the rest is returned as zero.  CUDA tensors take the fused path.  A CPU tensor only occurs in the
+    `-m "not gpu"` host-logic tests, which run the module tree with injected oracle ops (PWCFlow(ops=...)) to check the
+    wiring against the reference's goldens without a GPU; bench.py's CPU arm does not come through here (it runs
+    oracle/cpu_nets.py, which imports nothing from this package)."""
     if not x.is_cuda:
         return func.leaky_relu(conv(x), negative_slope=negative_slope)
     if conv.groups != 1 or conv.padding_mode != "zeros":

@@ -46,17 +46,6 @@ def matrix_vector_product_T_general(A, X, k=1):
     return _StencilMV.apply(A, X, k, True)
 
 
-def _pack(A, B, C, D):
-    """k=1 stencil given as four arrays -> the (N, 8, M, N) tap layout of the general product."""
-    K, L, M, N = A.shape
-    z = A.new_zeros(K, L, M, N)
-    Bp, Cp, Dp = z.clone(), z.clone(), z.clone()
-    Bp[:, :, :, :-1] = B
-    Cp[:, :, :-1, :] = C
-    Dp[:, :, :-1, :-1] = D
-    return A, Bp, Cp, Dp
-
-
 def matrix_vector_product(A, B, C, D, X):
     """triag_solve.py:20-28 (|D|C| / |B|A| stencil), channels handled independently."""
     B_Y = torch.nn.functional.pad(B * X[:, :, :, 0:-1], (1, 0))

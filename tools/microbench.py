@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--flow", default="both", choices=["iid", "smooth", "wild", "both"],
                     help="warp flow field: iid N(0,2^2) px per pixel (config 5, worst case for gathers) or a smooth field "
                          "(1/8-resolution N(0,2^2) noise, bilinearly upsampled: what a flow network produces)")
+    ap.add_argument("--warp-variant", type=int, default=0, help="debug hook 3: warp backward tuning variants")
     ap.add_argument("--census-variant", type=int, default=0, help="debug hook 5: 1 = per-pixel census kernels, 8..64 = strip height of the pair-symmetric ones")
     args = ap.parse_args()
     from arflow_b200 import _lib
@@ -174,6 +175,7 @@ def main():
     lib.arf_debug_set(1, args.variant)
     lib.arf_debug_set(2, args.probe)
     lib.arf_debug_set(5, args.census_variant)
+    lib.arf_debug_set(3, args.warp_variant)
     hbm, src = peaks()
     rows = []
 

@@ -15,21 +15,23 @@ prof () {  # name kernel-regex microbench-args...
       -o $OUT/${name}_${TAG} -f python tools/microbench.py "$@" > $OUT/ncu_${name}.log 2>&1
   tail -1 $OUT/plain_${name}.log
 }
+if [ "${TAG#r1}" != "$TAG" ]; then     # round-1 kernel names
 prof corr_fwd corr_fwd_md4 corr_fwd --shapes 64x32x96x128
 prof corr_bwd corr_bwd_md4 corr_bwd --shapes 64x32x96x128
 prof warp_fwd warp_fwd_kernel warp --flow smooth --shapes 64x32x96x128
-prof warp_gfield warp_gfield_win warp --flow smooth --shapes 64x32x96x128
-prof warp_gx warp_gx_csr warp --flow smooth --shapes 64x32x96x128
-prof warp_bwd_direct 'warp_bwd_kernel<8>' warp --flow smooth --shapes 16x32x96x128
 prof census_fwd census_fwd_kernel census --shapes 8x3x384x512
 prof census_bwd census_bwd_kernel census --shapes 8x3x384x512
+else
+prof corr_fwd corr_fwd_md4_p2 corr_fwd --shapes 64x32x96x128
+prof corr_fwd_cfg2 corr_fwd_md4_p2 corr_fwd --shapes 16x32x96x128
+prof corr_bwd corr_bwd_md4 corr_bwd --shapes 64x32x96x128
+prof corr_bwd_cfg2 corr_bwd_md4 corr_bwd --shapes 16x32x96x128
+prof warp_fwd warp_fwd_kernel warp --flow smooth --shapes 16x32x96x128
+prof warp_bwd_gx warp_bwd_lean warp --flow smooth --shapes 16x32x96x128
+prof census_fwd census_fwd_sym census --shapes 8x3x384x512
+prof census_bwd census_bwd_sym census --shapes 8x3x384x512
+fi
 prof stencil_fwd 'stencil_mv_kernel' stencil
 prof stencil_bwd 'stencil_mv_bwd_kernel' stencil
 prof trisolve trisolve_scan_kernel stencil
-prof flowhead_fwd conv3x3_small_fwd_kernel smallconv
-prof flowhead_bwd conv3x3_small_bwd_kernel smallconv
-prof first_wgrad conv3x3s2_first_wgrad_kernel smallconv
-prof epilogue_fwd bias_leaky_nhwc_fwd_kernel glue
-prof epilogue_bwd bias_leaky_nhwc_bwd_kernel glue
-prof nhwc_pack nhwc_part_kernel glue
 ls -la $OUT/*_${TAG}.ncu-rep
