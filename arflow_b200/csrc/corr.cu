@@ -548,6 +548,12 @@ corr_fwd_md4_p2(const __grid_constant__ CUtensorMap map1, const __grid_constant_
 // Item shapes in use (arf_corr_bwd picks by rounds x round time): <2,4> = 32x16 px x 32 channels, 8 consumer warps, one
 // CTA per SM, for problems that fill the machine with such items; <2,2> (16 channels) and <1,4> (32x8 px) for the coarse
 // pyramid levels, where two launches of the big item left most SMs idle behind a fixed ~35 us (16x32x24x32: 36 -> 13 us).
+// Round-2 measurements (ncu, profiles/r2_corr_bwd_cfg2_ncu.txt): FMA pipe 36 %, LSU 48 %, 9 resident warps.  The loop
+// spends 72 + 8 x 16 LDS.32 slots (at ~1.45 cycles each) per 576 FMAs, which caps the FMA pipe near 50 %.  Tried: the
+// same item with 4 rows per warp and 16 consumer warps at 96 registers (more LDS per FMA: 0.46 instead of 0.35) -
+// 334 vs 320 us at 64x32x96x128, i.e. occupancy buys nothing, the LDS slot count is the bound here too.  The forward
+// kernel's pair-shared operands do not carry over cheaply: the 2 x 36 gradient values of a displacement PAIR have to
+// sit in registers next to the accumulators, which leaves 8 channels per warp (0.29 LDS per FMA, -16 %) at 10 warps.
 constexpr int kBCg = 8;                  // channels per warp
 
 template <int RG, int CG, int STG>

@@ -59,7 +59,7 @@ CONFIGS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
@@ -833,6 +833,16 @@ def main_b200(args):
                            "fp32_frac": q["flops"] / sec / 1e12 / pk["fp32_tflops"],
                            "mufu_frac": q["mufu"] / sec / 1e9 / pk["mufu_gops"]})
         kernels["_by_shape"] = shapes
+        # every HOT-PATH (entry point, shape) of the step, in situ: the table the metric's "% of roofline" refers to
+        hot_shapes = []
+        for (name, label), q in sorted(per_shape.items(), key=lambda kv: -kv[1]["ms"]):
+            if name not in HOTPATH or q["bytes"] <= 0:
+                continue
+            r = roof_entry("%s [%s]" % (name, label), q["bytes"] / q["calls"], q["flops"] / q["calls"], q["mufu"] / q["calls"],
+                           q["ms"] * 1e-3 / q["calls"], pk)
+            hot_shapes.append({"call": r["kernel"], "us_per_launch": r["us"], "launches_per_step": q["calls"] / n_prof,
+                               "bound": r["bound"], "frac": r["frac"]})
+        kernels["_hot_by_shape"] = hot_shapes
         hot_us = sum(v["us_per_step"] for n, v in kernels.items() if n != "_by_shape" and v["hot_path"])
         kernels["_hot_path_us_per_step"] = hot_us
         if not args.no_hotpath:
