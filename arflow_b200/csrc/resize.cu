@@ -95,6 +95,89 @@ __global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict
     }
 }
 
+// ------------------------------------------------------------------ exact x2 up-sampling (align_corners = False) ---
+// upsample(flow, is_flow=True) of every pyramid level and the two x2 steps to full resolution (uflow_model.py:220,
+// 343-344) are all this one geometry.  Same arithmetic as the general kernels - the tap indices and weights still come
+// from src_index, and the backward adds its taps in the same order, so results are bit-identical - but the work is
+// laid out for the geometry: forward, a thread produces the two outputs above one source pixel from 2 x 3 loads and
+// stores them as one float2 (no per-pixel div / mod); backward, a thread gathers its fixed 4 x 4 candidate window
+// instead of deriving a candidate range with floor / ceil and walking it (the general kernel: ~400 instructions per
+// input pixel, 59 us for 32 planes of 192 x 256 -> 384 x 512; the window form: 16 loads and FMAs).
+__global__ void __launch_bounds__(256) resize_up2_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, ResizeGeom g) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;     // source column; outputs 2k, 2k + 1
+    const int oy = blockIdx.y;
+    if (k >= g.Wi) return;
+    int y0, y1, xa0, xa1, xb0, xb1;
+    float hy0, hy1, wa0, wa1, wb0, wb1;
+    src_index(oy, g.rh, g.Hi, 0, y0, y1, hy0, hy1);
+    src_index(2 * k, g.rw, g.Wi, 0, xa0, xa1, wa0, wa1);
+    src_index(2 * k + 1, g.rw, g.Wi, 0, xb0, xb1, wb0, wb1);
+    const size_t ip = (size_t)g.Hi * g.Wi, op = (size_t)g.Ho * g.Wo;
+    for (unsigned n = blockIdx.z; n < (unsigned)g.N; n += gridDim.z) {
+        const float* r0 = in + n * ip + (size_t)y0 * g.Wi;
+        const float* r1 = in + n * ip + (size_t)y1 * g.Wi;
+        const float va = hy0 * (wa0 * __ldg(r0 + xa0) + wa1 * __ldg(r0 + xa1)) + hy1 * (wa0 * __ldg(r1 + xa0) + wa1 * __ldg(r1 + xa1));
+        const float vb = hy0 * (wb0 * __ldg(r0 + xb0) + wb1 * __ldg(r0 + xb1)) + hy1 * (wb0 * __ldg(r1 + xb0) + wb1 * __ldg(r1 + xb1));
+        *reinterpret_cast<float2*>(out + n * op + (size_t)oy * g.Wo + 2 * k) = make_float2(va * g.mul, vb * g.mul);
+    }
+}
+
+__global__ void __launch_bounds__(256) resize_up2_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, ResizeGeom g) {
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int iy = blockIdx.y;
+    if (ix >= g.Wi) return;
+    // candidate outputs 2i-1 .. 2i+2 per axis; weight with which candidate j referenced source index i (0 if it did not)
+    float wy[4], wx[4];
+    int oys[4], oxs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int a0, a1;
+        float l0, l1;
+        const int oy = 2 * iy - 1 + j, ox = 2 * ix - 1 + j;
+        const bool vy = oy >= 0 && oy < g.Ho, vx = ox >= 0 && ox < g.Wo;
+        oys[j] = vy ? oy : 0;
+        oxs[j] = vx ? ox : 0;
+        src_index(oys[j], g.rh, g.Hi, 0, a0, a1, l0, l1);
+        wy[j] = vy ? (a0 == iy ? l0 : 0.f) + (a1 == iy ? l1 : 0.f) : 0.f;
+        src_index(oxs[j], g.rw, g.Wi, 0, a0, a1, l0, l1);
+        wx[j] = vx ? (a0 == ix ? l0 : 0.f) + (a1 == ix ? l1 : 0.f) : 0.f;
+    }
+    const size_t ip = (size_t)g.Hi * g.Wi, op = (size_t)g.Ho * g.Wo;
+    for (unsigned n = blockIdx.z; n < (unsigned)g.N; n += gridDim.z) {
+        const float* go = gout + n * op;
+        float v[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[j][i] = __ldg(go + (size_t)oys[j] * g.Wo + oxs[i]);
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (wy[j] == 0.f) continue;
+            float row = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (wx[i] != 0.f) row = fmaf(wx[i], v[j][i], row);
+            acc = fmaf(wy[j], row, acc);
+        }
+        gin[n * ip + (size_t)iy * g.Wi + ix] = acc * g.mul;
+    }
+}
+
+static inline bool is_up2(const ResizeGeom& g) {
+    return !g.align && g.Ho == 2 * g.Hi && g.Wo == 2 * g.Wi && g.rh == 0.5f && g.rw == 0.5f && g.Ho <= 65535 && g.Hi >= 2 &&
+           g.Wi >= 2;
+}
+// rows on grid.y, planes strided over grid.z
+static inline dim3 up2_grid(int cols, int rows, long long planes) {
+    const long long bx = (cols + 255) / 256;
+    long long bz = (16LL * ARF_NUM_SMS + bx * rows - 1) / (bx * rows);
+    if (bz > planes) bz = planes;
+    if (bz > 65535) bz = 65535;
+    if (bz < 1) bz = 1;
+    return dim3((unsigned)bx, (unsigned)rows, (unsigned)bz);
+}
+
 // grid for the two kernels: x covers one plane, y the planes (capped; both loops are strided)
 static inline dim3 resize_grid(long long pix_per_plane, long long planes) {
     long long bx = (pix_per_plane + 255) / 256;
@@ -124,7 +207,10 @@ extern "C" int arf_resize_bilinear_fwd(const float* in, float* out, long long pl
     ResizeGeom g;
     int rc = make_geom(g, planes, Hi, Wi, Ho, Wo, rh, rw, mul, align_corners);
     if (rc) return rc;
-    resize_fwd_kernel<<<resize_grid((long long)Ho * Wo, planes), 256, 0, (cudaStream_t)stream>>>(in, out, g);
+    if (is_up2(g) && ((uintptr_t)out % 8 == 0))
+        resize_up2_fwd_kernel<<<up2_grid(Wi, Ho, planes), 256, 0, (cudaStream_t)stream>>>(in, out, g);
+    else
+        resize_fwd_kernel<<<resize_grid((long long)Ho * Wo, planes), 256, 0, (cudaStream_t)stream>>>(in, out, g);
     ARF_CHECK_LAUNCH();
     return ARF_OK;
 }
@@ -135,7 +221,10 @@ extern "C" int arf_resize_bilinear_bwd(const float* gout, float* gin, long long 
     ResizeGeom g;
     int rc = make_geom(g, planes, Hi, Wi, Ho, Wo, rh, rw, mul, align_corners);
     if (rc) return rc;
-    resize_bwd_kernel<<<resize_grid((long long)Hi * Wi, planes), 256, 0, (cudaStream_t)stream>>>(gout, gin, g);
+    if (is_up2(g))
+        resize_up2_bwd_kernel<<<up2_grid(Wi, Hi, planes), 256, 0, (cudaStream_t)stream>>>(gout, gin, g);
+    else
+        resize_bwd_kernel<<<resize_grid((long long)Hi * Wi, planes), 256, 0, (cudaStream_t)stream>>>(gout, gin, g);
     ARF_CHECK_LAUNCH();
     return ARF_OK;
 }

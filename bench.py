@@ -843,7 +843,7 @@ def main_b200(args):
             hot_shapes.append({"call": r["kernel"], "us_per_launch": r["us"], "launches_per_step": q["calls"] / n_prof,
                                "bound": r["bound"], "frac": r["frac"]})
         kernels["_hot_by_shape"] = hot_shapes
-        hot_us = sum(v["us_per_step"] for n, v in kernels.items() if n != "_by_shape" and v["hot_path"])
+        hot_us = sum(v["us_per_step"] for n, v in kernels.items() if not n.startswith("_") and v["hot_path"])
         kernels["_hot_path_us_per_step"] = hot_us
         if not args.no_hotpath:
             del eager

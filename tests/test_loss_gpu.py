@@ -50,6 +50,25 @@ def test_resize_golden():
             assert_close(gi, g["down%d_%d_grad0_f64" % (s, is_flow)], RTOL_GRAD)
 
 
+@pytest.mark.parametrize("shape", [(2, 2, 7, 5), (3, 2, 2, 2), (1, 3, 24, 32), (4, 2, 96, 128), (1, 2, 33, 130)])
+def test_upsample_x2_fast_path_vs_aten_fp64(shape):
+    """The exact x2 geometry (every flow up-sampling of the networks) runs on its own kernels; they must agree with
+    ATen's float64 bilinear interpolation, values and gradient, at odd sizes, at the 2 x 2 minimum and at full size."""
+    from arflow_b200 import uflow_utils as uu
+    gen = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=gen)
+    w = torch.randn(shape[0], shape[1], 2 * shape[2], 2 * shape[3], generator=gen)
+    for is_flow in (False, True):
+        xc = x.cuda().requires_grad_(True)
+        out = uu.upsample(xc, is_flow, scale_factor=2.0)
+        (gi,) = torch.autograd.grad((out * w.cuda()).sum(), [xc])
+        xd = x.double().requires_grad_(True)
+        ref = torch.nn.functional.interpolate(xd, scale_factor=2.0, mode="bilinear", align_corners=False) * (2.0 if is_flow else 1.0)
+        (gr,) = torch.autograd.grad((ref * w.double()).sum(), [xd])
+        assert_close(out, ref, RTOL_VALUE, "x2 value")
+        assert_close(gi, gr, RTOL_GRAD, "x2 gradient")
+
+
 def test_census_golden():
     from arflow_b200 import loss_blocks as lb
     from arflow_b200 import uflow_utils as uu
