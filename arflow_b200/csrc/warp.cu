@@ -24,6 +24,15 @@
 //  * the source gradient is bound by the L2's reduction throughput (~460 G lane-adds/s; 4 per element and channel):
 //    merging lane L's east taps into lane L+1's west taps halves the lanes but not the requests: 220 -> 199 us.
 //    fp32 shared-memory atomics run at ~8 lanes/clk/SM (tools/peaks.cu), 4.7x the global rate in aggregate.
+//  * round 2, measured and dropped: (a) software-pipelining the channel chunks (two chunks in flight): 64 vs 56 us at
+//    16x32x96x128; (b) 64 registers x 4 CTAs/SM, or 8 channels in flight: 56-62 us - the kernel is not occupancy-bound;
+//    (c) a source-gradient-only kernel whose threads own 4 vertically adjacent pixels and add coinciding south / north
+//    and east / west taps in registers before the reduction (1.25 reductions per pixel and channel on a regular flow):
+//    correct, but 73 vs 56 us on the benchmark's smooth flow (gradient ~0.35 px/px: only ~45 % of the row pairs and
+//    ~65 % of the lane pairs line up, ~2.3 reductions per pixel and channel) - register pre-aggregation pays only on
+//    flows far smoother than the ones a network under training produces.  tools/red_probe.cu: the L2 retires ~630 G
+//    fp32 reductions per second, scalar or .v4, coalesced or not, so the remaining lever is a shared-memory window per
+//    output tile (fp32 shared atomics: 2.2 T/s) flushed with one reduction per touched element (~1.3-1.6).
 #include "common.cuh"
 
 thread_local int g_warp_variant = 0;   // test hook slot (arf_debug_set key 3), unused since the window kernels were removed
