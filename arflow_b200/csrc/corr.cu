@@ -416,8 +416,8 @@ __device__ __forceinline__ unsigned long long lds_pair(const float* p) {
 
 constexpr int kPW = 5;   // displacement-pair warps per row group
 
-template <int R, int RG, int kStg>
-__global__ void __launch_bounds__(32 * (kPW * RG + 1), 1)
+template <int R, int RG, int kStg, int kMinB = 1>
+__global__ void __launch_bounds__(32 * (kPW * RG + 1), kMinB)
 corr_fwd_md4_p2(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                 float* __restrict__ out, int B, int C, int H, int W, int tiles_x, int tiles_y, float inv_c, int probe) {
     // probe (tuning only): 2 = skip the output stores
@@ -859,33 +859,42 @@ extern "C" int arf_corr_fwd(const float* f1, const float* f2, float* out, int B,
         const float inv_c = 1.0f / (float)C;
         const bool tma = !g_force_no_tma && arf::tma_ok_nchw(f1, W) && arf::tma_ok_nchw(f2, W);
         const long long sms = ARF_NUM_SMS;
-        // Two tiled kernels.  "p2" (pair-shared 64-bit operands, 32x12 tiles, one 16-warp CTA per SM) needs TMA and wins
-        // whenever its tile count fills the machine as well as the 32x8 tiles of the column-thread kernel (two CTAs per
-        // SM) do.  A launch lasts rounds x tile time; measured tile times per channel and tile row (B200, tools/
-        // microbench.py corr_fwd --variant 30 | 31): 0.0235 us (p2) against 0.0529 us with two CTAs sharing an SM.
-        // E.g. 64x32x96x128: 126 vs 149 us, 64x96x24x32: 26 vs 38, 8x64x56x128 (160 p2 tiles = 2 rounds): 35 vs 28.
+        // Three tiled launches.  "p2" (pair-shared 64-bit operands) needs TMA and runs with 32x12 tiles (one 16-warp CTA per
+        // SM) or, for problems that would leave SMs idle that way (a coarse pyramid level, batch 1), with 32x4 tiles (one
+        // row group, 6 warps, two CTAs per SM); the column-thread kernel has 32x8 tiles (two CTAs per SM) and serves the
+        // tensors TMA cannot describe.  A launch lasts (tiles on the busiest SM) x (tile rows) x (time per row and
+        // channel); measured on B200 (tools/microbench.py corr_fwd --variant 30 | 31 | 32): 0.0235 us (p2), 0.025 (p2
+        // small), 0.0529 per CTA with two column-thread CTAs sharing an SM.  E.g. 64x32x96x128: 126 (p2) / 149 us (column);
+        // 16x96x24x32: 25 / 25 / 15 (small tiles); 1x64x48x80: 18 / 19 / 11; 8x64x56x128 (160 p2 tiles = 2 rounds): 35 / 28.
         const long long n_p2 = (long long)tiles_x * arf_cdiv(H, 12) * B, n_ct = (long long)tiles_x * arf_cdiv(H, kTH) * B;
-        if (n_ct > 0x7fffffffLL) return ARF_EINVAL;
+        const long long n_p2s = (long long)tiles_x * arf_cdiv(H, 4) * B;
+        if (n_p2s > 0x7fffffffLL) return ARF_EINVAL;
         const double t_p2 = (double)((n_p2 + sms - 1) / sms) * 12 * 0.0235;
+        const double t_p2s = (double)((n_p2s + sms - 1) / sms) * 4 * 0.025;
         const double t_ct = (double)((n_ct + 2 * sms - 1) / (2 * sms)) * kTH * 0.0529;
-        bool use_p2 = tma && t_p2 < 0.97 * t_ct;
-        if (g_variant == 30) use_p2 = tma;          // tuning hooks: force either kernel
-        if (g_variant == 31) use_p2 = false;
-        if (use_p2) {
-            constexpr int R = 4, RG = 3, STG = 4;
-            CUtensorMap m1, m2;
-            if (arf::make_map_nchw(&m1, f1, B, C, H, W, kTW, R * RG, 8) &&
-                arf::make_map_nchw(&m2, f2, B, C, H, W, kHW, R * RG + 2 * kMD, 8)) {
-                auto kern = corr_fwd_md4_p2<R, RG, STG>;
-                ARF_ENSURE_SMEM(kern, (fwd_p2_smem<R * RG, 8>(STG)));
-                const int tiles_y = arf_cdiv(H, R * RG);
-                const int grid = (int)(n_p2 < sms ? n_p2 : sms);
-                kern<<<grid, 32 * (kPW * RG + 1), fwd_p2_smem<R * RG, 8>(STG), st>>>(m1, m2, out, B, C, H, W, tiles_x,
-                                                                                     tiles_y, inv_c, g_probe);
-                ARF_CHECK_LAUNCH();
-                return ARF_OK;
-            }
-        }
+        bool use_p2s = tma && t_p2s < 0.97 * t_p2 && t_p2s < 0.97 * t_ct;
+        bool use_p2 = tma && !use_p2s && t_p2 < 0.97 * t_ct;
+        if (g_variant == 30) { use_p2 = tma; use_p2s = false; }          // tuning hooks: force one of the three
+        if (g_variant == 31) { use_p2 = false; use_p2s = false; }
+        if (g_variant == 32) { use_p2s = tma; use_p2 = false; }
+#define ARF_LAUNCH_P2(R, RG, STG, MINB, NT)                                                                          \
+    do {                                                                                                             \
+        CUtensorMap m1, m2;                                                                                          \
+        if (arf::make_map_nchw(&m1, f1, B, C, H, W, kTW, R * RG, 8) &&                                               \
+            arf::make_map_nchw(&m2, f2, B, C, H, W, kHW, R * RG + 2 * kMD, 8)) {                                     \
+            auto kern = corr_fwd_md4_p2<R, RG, STG, MINB>;                                                           \
+            ARF_ENSURE_SMEM(kern, (fwd_p2_smem<R * RG, 8>(STG)));                                                    \
+            const int tiles_y = arf_cdiv(H, R * RG);                                                                 \
+            const int grid = (int)((NT) < (MINB) * sms ? (NT) : (MINB) * sms);                                       \
+            kern<<<grid, 32 * (kPW * RG + 1), fwd_p2_smem<R * RG, 8>(STG), st>>>(m1, m2, out, B, C, H, W, tiles_x,   \
+                                                                                 tiles_y, inv_c, g_probe);           \
+            ARF_CHECK_LAUNCH();                                                                                      \
+            return ARF_OK;                                                                                           \
+        }                                                                                                            \
+    } while (0)
+        if (use_p2s) ARF_LAUNCH_P2(4, 1, 4, 2, n_p2s);
+        if (use_p2) ARF_LAUNCH_P2(4, 3, 4, 1, n_p2);
+#undef ARF_LAUNCH_P2
         const int tiles_y = arf_cdiv(H, kTH);
         const long long ntiles = n_ct;
         CUtensorMap m1, m2;

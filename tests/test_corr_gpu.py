@@ -105,8 +105,8 @@ def test_cp_async_staging_path_matches_tma_path(oracle, shape):
 
 @pytest.mark.parametrize("shape", [(2, 32, 24, 32), (3, 20, 50, 68), (1, 7, 37, 100), (2, 196, 12, 16), (1, 64, 13, 36)])
 def test_both_tiled_forward_kernels_vs_oracle(oracle, shape):
-    """arf_corr_fwd routes between two tiled kernels by a cost model (32x12 tiles with lane pairs sharing 64-bit
-    operands / 32x8 column-thread tiles); the debug hook forces either one.  Ragged heights, widths that leave partial
+    """arf_corr_fwd routes between three tiled launches by a cost model (32x12 or 32x4 tiles with lane pairs sharing
+    64-bit operands / 32x8 column-thread tiles); the debug hook forces each in turn.  Ragged heights, widths that leave partial
     tiles and channel counts that leave partial stages: both must match the C oracle and each other bit for bit (same
     FMA order per accumulator)."""
     from arflow_b200 import _lib
@@ -115,14 +115,14 @@ def test_both_tiled_forward_kernels_vs_oracle(oracle, shape):
     f1, f2 = torch.randn(shape, generator=gen).cuda(), torch.randn(shape, generator=gen).cuda()
     ref = oracle.corr_fwd_c(f1.cpu(), f2.cpu())
     outs = []
-    for variant in (30, 31):
+    for variant in (30, 31, 32):
         _lib.call("arf_debug_set", 1, variant)
         try:
             outs.append(compute_cost_volume(f1, f2, 4))
         finally:
             _lib.call("arf_debug_set", 1, 0)
         assert_close(outs[-1], ref, RTOL_VALUE, "variant %d" % variant)
-    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
 # Full BASELINE sizes against the C oracle (double accumulation): config 2's finest level, and batch 16 at the

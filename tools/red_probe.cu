@@ -27,6 +27,26 @@ __global__ void red1x2(float* p, size_t n) {
     }
 }
 
+// TMA bulk reduction: every CTA adds a shared-memory tile of `tile_bytes` into its own global regions, chunk by chunk
+// (cp.reduce.async.bulk.global.shared::cta.add.f32) - the flush a shared-memory accumulation window would use.
+__global__ void red_bulk(float* p, size_t n, int tile_floats) {
+    extern __shared__ __align__(128) float tile[];
+    for (int i = threadIdx.x; i < tile_floats; i += blockDim.x) tile[i] = 1.0f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned src = (unsigned)__cvta_generic_to_shared(tile);
+        int k = 0;
+        for (size_t i = (size_t)blockIdx.x * tile_floats; i + tile_floats <= n; i += (size_t)gridDim.x * tile_floats) {
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                         ::"l"(p + i), "r"(src), "r"(tile_floats * 4) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (++k % 8 == 0) asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
 template <typename F>
 float time_ms(F f) {
     cudaEvent_t s, e;
@@ -56,6 +76,11 @@ int main() {
     float a2 = time_ms([&] { red1<<<blocks, threads>>>(p, m); });
     float b3 = time_ms([&] { red4<<<blocks, threads>>>(p, m); });
     float d2 = time_ms([&] { red1x2<<<blocks, threads>>>(p, m); });
+    float e1 = time_ms([&] { red_bulk<<<blocks, 128, 4096>>>(p, n, 1024); });
+    float e2 = time_ms([&] { red_bulk<<<blocks, 128, 512>>>(p, n, 128); });
+    float e3 = time_ms([&] { red_bulk<<<blocks, 128, 4096>>>(p, m, 1024); });
+    printf("{\"bulk_reduce_4KB_Gelem_s\": %.1f, \"bulk_reduce_512B_Gelem_s\": %.1f, \"l2_bulk_reduce_4KB_Gelem_s\": %.1f}\n",
+           n / e1 / 1e6, n / e2 / 1e6, m / e3 / 1e6);
     printf("{\"red_f32_Gelem_s\": %.1f, \"red_v2_Gelem_s\": %.1f, \"red_v4_Gelem_s\": %.1f, \"st_f32_Gelem_s\": %.1f, "
            "\"red_f32_pair_Gadds_s\": %.1f, \"l2_red_f32_Gelem_s\": %.1f, \"l2_red_v4_Gelem_s\": %.1f, "
            "\"l2_red_f32_pair_Gadds_s\": %.1f}\n",
