@@ -80,6 +80,40 @@ resampler_bwd_kernel(const float* __restrict__ data, const float* __restrict__ w
     }
 }
 
+// Few channels (images: C = 3): a warp per sample point leaves 29 lanes idle (600 us for 8 x 384 x 512 x 3); here a THREAD
+// owns the point and walks its channels, the coordinate gradients stay in registers.
+__global__ void __launch_bounds__(256)
+resampler_bwd_thread_kernel(const float* __restrict__ data, const float* __restrict__ wxp, const float* __restrict__ wyp,
+                            long long wstride, const float* __restrict__ gout, float* __restrict__ gdata,
+                            float* __restrict__ gwx, float* __restrict__ gwy, long long gwstride, RsGeom g) {
+    const long long npts = (long long)g.B * g.P;
+    for (long long pt = blockIdx.x * (long long)blockDim.x + threadIdx.x; pt < npts; pt += (long long)gridDim.x * blockDim.x) {
+        const int b = pt / g.P;
+        const float wx = __ldg(wxp + pt * wstride), wy = __ldg(wyp + pt * wstride);
+        int x0, x1, y0, y1; float fx, fy; bool ok[4];
+        taps(wx, wy, g.W, g.H, x0, x1, y0, y1, fx, fy, ok);
+        const size_t base = (size_t)b * g.H * g.W * g.C;
+        const size_t o00 = base + ((size_t)y0 * g.W + x0) * g.C, o01 = base + ((size_t)y0 * g.W + x1) * g.C;
+        const size_t o10 = base + ((size_t)y1 * g.W + x0) * g.C, o11 = base + ((size_t)y1 * g.W + x1) * g.C;
+        float ax = 0.f, ay = 0.f;
+        for (int c = 0; c < g.C; ++c) {
+            const float go = __ldg(gout + pt * g.C + c);
+            const float v00 = ok[0] ? __ldg(data + o00 + c) : 0.f, v01 = ok[1] ? __ldg(data + o01 + c) : 0.f;
+            const float v10 = ok[2] ? __ldg(data + o10 + c) : 0.f, v11 = ok[3] ? __ldg(data + o11 + c) : 0.f;
+            ax += go * ((v01 - v00) * (1.f - fy) + (v11 - v10) * fy);
+            ay += go * ((v10 * (1.f - fx) + v11 * fx) - (v00 * (1.f - fx) + v01 * fx));
+            if (gdata) {
+                if (ok[0]) atomicAdd(gdata + o00 + c, go * (1.f - fx) * (1.f - fy));
+                if (ok[1]) atomicAdd(gdata + o01 + c, go * fx * (1.f - fy));
+                if (ok[2]) atomicAdd(gdata + o10 + c, go * (1.f - fx) * fy);
+                if (ok[3]) atomicAdd(gdata + o11 + c, go * fx * fy);
+            }
+        }
+        if (gwx) gwx[pt * gwstride] = ax;
+        if (gwy) gwy[pt * gwstride] = ay;
+    }
+}
+
 }  // namespace
 
 /* data: (B,H,W,C) NHWC; warp_x, warp_y: B*P coordinates read at stride `wstride` elements (1 for separate
@@ -105,9 +139,14 @@ extern "C" int arf_resampler_bwd(const float* data, const float* warp_x, const f
         if (e != cudaSuccess) return (int)e;
     }
     RsGeom g{B, H, W, C, P};
-    long long threads = (long long)B * P * 32;
-    resampler_bwd_kernel<<<arf_grid_1d(threads, 256), 256, 0, st>>>(data, warp_x, warp_y, wstride, gout, gdata, gwx,
-                                                                   gwy, gwstride > 0 ? gwstride : 1, g);
+    if (C <= 8) {
+        resampler_bwd_thread_kernel<<<arf_grid_1d((long long)B * P, 256), 256, 0, st>>>(
+            data, warp_x, warp_y, wstride, gout, gdata, gwx, gwy, gwstride > 0 ? gwstride : 1, g);
+    } else {
+        long long threads = (long long)B * P * 32;
+        resampler_bwd_kernel<<<arf_grid_1d(threads, 256), 256, 0, st>>>(data, warp_x, warp_y, wstride, gout, gdata, gwx,
+                                                                       gwy, gwstride > 0 ? gwstride : 1, g);
+    }
     ARF_CHECK_LAUNCH();
     return ARF_OK;
 }

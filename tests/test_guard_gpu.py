@@ -169,3 +169,35 @@ def test_substitution_stays_in_bounds(shape, upper):
     assert lib.arf_trisolve(A.data_ptr(), ptr(Bm), ptr(Cm), Dm.data_ptr() if Dm is not None else None, X.data_ptr(),
                             Y.data_ptr(), S, M, Nn, upper, _cs()) == 0
     ar.check("substitution %s upper=%d" % (shape, upper))
+
+
+@pytest.mark.parametrize("wild", [False, True])
+def test_resampler_stays_in_bounds(wild):
+    """NHWC resampler, interleaved (x, y) coordinates (element stride 2); wild = coordinates far outside the image,
+    +-inf and NaN among them: such taps must contribute nothing and write nothing."""
+    from arflow_b200 import _lib
+    lib = _lib.load()
+    B, H, W, C = 2, 13, 21, 5
+    g = torch.Generator().manual_seed(7)
+    ar = Arena()
+    data = ar.inp(torch.randn(B, H, W, C, generator=g))
+    xy = torch.rand(B, H, W, 2, generator=g) * torch.tensor([W - 1.0, H - 1.0])
+    if wild:
+        xy = (xy - 5.0) * 40.0
+        xy.view(-1)[::7] = float("inf")
+        xy.view(-1)[3::11] = float("-inf")
+        xy.view(-1)[5::13] = float("nan")
+        xy.view(-1)[1::17] = 3.0e9
+    wxy = ar.inp(xy)
+    go = ar.inp(torch.randn(B, H * W, C, generator=g))
+    out, gd, gw = ar.out(B, H * W, C), ar.out(B, H, W, C), ar.out(B, H, W, 2)
+    wp, gp = wxy.data_ptr(), gw.data_ptr()
+    assert lib.arf_resampler_fwd(data.data_ptr(), wp, wp + 4, 2, out.data_ptr(), B, H, W, C, H * W, _cs()) == 0
+    assert lib.arf_resampler_bwd(data.data_ptr(), wp, wp + 4, 2, go.data_ptr(), gd.data_ptr(), gp, gp + 4, 2, B, H, W, C,
+                                 H * W, _cs()) == 0
+    if wild:      # NaN / inf coordinates give NaN interpolation weights: only the guard bands are checked
+        torch.cuda.synchronize()
+        for raw, n in ar.bufs:
+            assert bool((raw[:GUARD] == SENT).all()) and bool((raw[GUARD + n + ((-n) % 4):] == SENT).all())
+    else:
+        ar.check("resampler")

@@ -213,6 +213,26 @@ def test_ssim_and_resampler_golden():
     assert_close(gw, g["resampler_grad1_f64"], RTOL_GRAD)
 
 
+@pytest.mark.parametrize("C", [3, 8, 12, 40])
+def test_resampler_both_backward_kernels_vs_oracle(oracle, C):
+    """arf_resampler_bwd owns a sample point by a thread (C <= 8) or by a warp (wider data); both against the float64
+    oracle (uflow_resampler.py:155-241), coordinates partly outside the image."""
+    from arflow_b200 import uflow_resampler as ur
+    gen = torch.Generator().manual_seed(C)
+    data = torch.randn(2, 9, 11, C, generator=gen)
+    warp = torch.rand(2, 5, 7, 2, generator=gen) * torch.tensor([13.0, 11.0]) - 1.5
+    w = torch.randn(2, 5, 7, C, generator=gen)
+    d64, w64 = data.double().requires_grad_(True), warp.double().requires_grad_(True)
+    ref = oracle.resampler(d64, w64[..., 0], w64[..., 1])
+    rd, rw = torch.autograd.grad((ref * w.double()).sum(), [d64, w64])
+    dc, wc = data.cuda().requires_grad_(True), warp.cuda().requires_grad_(True)
+    out = ur.resampler(dc, wc)
+    gd, gw = torch.autograd.grad((out * w.cuda()).sum(), [dc, wc])
+    assert_close(out, ref, RTOL_VALUE, "resampler")
+    assert_close(gd, rd, RTOL_GRAD, "d / d data")
+    assert_close(gw, rw, RTOL_GRAD, "d / d warp")
+
+
 @pytest.mark.parametrize("name", ["elbo_sparse", "elbo_diag"])
 def test_uflow_elbo_loss_golden(name):
     """UFlowElboLoss (non-diagonal stencil covariance, and diagonal with closed-form smoothness, out-of-frame

@@ -275,6 +275,104 @@ def main():
                 return make
             report("census_fwd", (B, 3, H, W), px * 32, px * 640, *time_graph(mkc("fwd"), px * 32))
             report("census_bwd", (B, 3, H, W), px * 44, px * 1280, *time_graph(mkc("bwd"), px * 44))
+    if args.what in ("loss", "all"):
+        # the remaining SURVEY §8(a) rows at the chairs_uflow loss shapes: SSIM (P2/P4), NHWC resampler (W3), masks (M1-M3),
+        # smoothness (S1), resize (U1), inverse_diagonal (T4)
+        B, H, W = 8, 384, 512
+        px = B * H * W
+
+        def mk_ssim(kind):
+            def make():
+                x, y = torch.rand(B * 3, H, W, device="cuda"), torch.rand(B * 3, H, W, device="cuda")
+                o1, o2 = torch.empty_like(x), torch.empty_like(x)
+                g1, g2 = torch.randn_like(x), torch.randn_like(x)
+                coef = torch.empty(5 * B * 3 * H * W, device="cuda")
+                gx, gy = torch.empty_like(x), torch.empty_like(x)
+                if kind == "fwd":
+                    return lambda: lib.arf_ssim_fwd(x.data_ptr(), y.data_ptr(), o1.data_ptr(), o2.data_ptr(), B * 3, H, W, 3, 0, 0, cs())
+                return lambda: lib.arf_ssim_bwd(x.data_ptr(), y.data_ptr(), g1.data_ptr(), g2.data_ptr(), coef.data_ptr(),
+                                                gx.data_ptr(), gy.data_ptr(), B * 3, H, W, 3, 0, 0, cs())
+            return make
+        report("ssim_fwd", (B, 3, H, W), px * 3 * 16, px * 3 * 90, *time_graph(mk_ssim("fwd"), px * 3 * 16))
+        report("ssim_bwd", (B, 3, H, W), px * 3 * 24, px * 3 * 200, *time_graph(mk_ssim("bwd"), px * 3 * 24))
+
+        def mk_res(kind):
+            def make():
+                data = torch.randn(B, H, W, 3, device="cuda")
+                wxy = torch.rand(B, H, W, 2, device="cuda") * torch.tensor([W - 1.0, H - 1.0], device="cuda")
+                out = torch.empty(B, H * W, 3, device="cuda")
+                go = torch.randn_like(out)
+                gd, gw = torch.empty_like(data), torch.empty_like(wxy)
+                wp = wxy.data_ptr()
+                # (the lambdas keep `wxy` alive: only its address is passed on)
+                if kind == "fwd":
+                    return lambda keep=wxy: lib.arf_resampler_fwd(data.data_ptr(), wp, wp + 4, 2, out.data_ptr(), B, H, W, 3, H * W, cs())
+                return lambda keep=wxy: lib.arf_resampler_bwd(data.data_ptr(), wp, wp + 4, 2, go.data_ptr(), gd.data_ptr(),
+                                                              gw.data_ptr(), gw.data_ptr() + 4, 2, B, H, W, 3, H * W, cs())
+            return make
+        report("resampler_fwd", (B, H, W, 3), px * (12 + 8 + 12), px * 3 * 8, *time_graph(mk_res("fwd"), px * 32))
+        report("resampler_bwd", (B, H, W, 3), px * (12 + 8 + 12 + 12 + 8), px * 3 * 16, *time_graph(mk_res("bwd"), px * 52))
+
+        hq, wq = H // 4, W // 4
+        pq = B * hq * wq
+
+        def mk_mask(kind):
+            def make():
+                fl = torch.randn(B, 2, hq, wq, device="cuda") * 3
+                fl2 = torch.randn(B, 2, hq, wq, device="cuda") * 3
+                m = torch.empty(B, 1, hq, wq, device="cuda")
+                gc = torch.randn(B, 1, hq, wq, device="cuda")
+                gf = torch.empty_like(fl)
+                if kind == "inside":
+                    return lambda: lib.arf_inside_mask(fl.data_ptr(), m.data_ptr(), B, hq, wq, 0, 0, cs())
+                if kind == "range":
+                    return lambda: lib.arf_range_map(fl.data_ptr(), m.data_ptr(), B, hq, wq, 0, cs())
+                if kind == "range_bwd":
+                    return lambda: lib.arf_range_map_bwd(fl.data_ptr(), gc.data_ptr(), gf.data_ptr(), B, hq, wq, 0, cs())
+                if kind == "count":
+                    return lambda: lib.arf_count_to_mask(gc.data_ptr(), m.data_ptr(), B * hq * wq, 0, 0.0, cs())
+                return lambda: lib.arf_occ_bidir(fl.data_ptr(), fl2.data_ptr(), m.data_ptr(), B, hq, wq, 0.01, 0.5, cs())
+            return make
+        for kind, nb in (("inside", 12), ("range", 16), ("range_bwd", 20), ("count", 8), ("occ_bidir", 20)):
+            report("mask_" + kind, (B, 2, hq, wq), pq * nb, 0, *time_graph(mk_mask(kind), pq * nb))
+
+        def mk_smooth(kind, order):
+            def make():
+                img = torch.rand(B, 3, hq, wq, device="cuda")
+                fl = torch.randn(B, 2, hq, wq, device="cuda")
+                npart = lib.arf_smooth_num_partials(B, hq, wq)
+                part, out = torch.empty(2 * npart, device="cuda"), torch.empty(1, device="cuda")
+                gl, gfl = torch.ones(1, device="cuda"), torch.empty_like(fl)
+                a = (B, 3, hq, wq, order, 1, 0, 0, 150.0, 1e-6, 1.0)
+                if kind == "fwd":
+                    return lambda: lib.arf_smooth_fwd(img.data_ptr(), fl.data_ptr(), out.data_ptr(), part.data_ptr(), *a, cs())
+                return lambda: lib.arf_smooth_bwd(img.data_ptr(), fl.data_ptr(), gl.data_ptr(), gfl.data_ptr(), *a, cs())
+            return make
+        for order in (1, 2):
+            report("smooth%d_fwd" % order, (B, 3, hq, wq), pq * 20, 0, *time_graph(mk_smooth("fwd", order), pq * 20))
+            report("smooth%d_bwd" % order, (B, 3, hq, wq), pq * 28, 0, *time_graph(mk_smooth("bwd", order), pq * 28))
+
+        for (N, Hi, Wi, Ho, Wo, tag) in ((32, 192, 256, 384, 512, "up2"), (16, 96, 128, 384, 512, "up4"), (24, 384, 512, 96, 128, "down4")):
+            def mk_rs(kind):
+                def make():
+                    a = torch.randn(N, Hi, Wi, device="cuda")
+                    b = torch.randn(N, Ho, Wo, device="cuda")
+                    r = (N, Hi, Wi, Ho, Wo, Hi / Ho, Wi / Wo, 1.0, 0)
+                    if kind == "fwd":
+                        return lambda: lib.arf_resize_bilinear_fwd(a.data_ptr(), b.data_ptr(), *r, cs())
+                    return lambda: lib.arf_resize_bilinear_bwd(b.data_ptr(), a.data_ptr(), *r, cs())
+                return make
+            nb = N * (Hi * Wi + Ho * Wo) * 4
+            report("resize_%s_fwd" % tag, (N, Hi, Wi), nb, 0, *time_graph(mk_rs("fwd"), nb))
+            report("resize_%s_bwd" % tag, (N, Hi, Wi), nb, 0, *time_graph(mk_rs("bwd"), nb))
+
+        def mk_inv():
+            S, M, Nn = 16, 24, 32
+            A = torch.rand(S, M, Nn, device="cuda") + 1.5
+            Bm, Cm = torch.randn(S, M, Nn - 1, device="cuda") * 0.3, torch.randn(S, M - 1, Nn, device="cuda") * 0.3
+            Hh = torch.empty(S, M, Nn, device="cuda")
+            return lambda: lib.arf_inv_diag(A.data_ptr(), Bm.data_ptr(), Cm.data_ptr(), Hh.data_ptr(), S, M, Nn, cs())
+        report("inv_diag", (16, 24, 32), 16 * 24 * 32 * 16, 0, *time_graph(mk_inv, 16 * 24 * 32 * 16))
     if args.what in ("stencil", "all"):
         for (N, k, H, W) in [(32, 3, 112, 256), (8, 3, 96, 128)]:
             px = N * H * W
