@@ -388,6 +388,9 @@ corr_fwd_md4(const __grid_constant__ CUtensorMap map1, const __grid_constant__ C
 //     3 row groups); 144 us with R = 6 x 2 (11 warps, 168 registers), 213 us with R = 8 x 1 (6 warps); its loop without
 //     the output stores 99 us; scalar FFMAs instead of FFMA2 165 us; starting the row groups one stage apart so that
 //     their epilogues do not coincide 140 us (worse: the groups then compete for the LSU instead of sharing L1 lines).
+//     The epilogue (127 - 99 us) is the SM -> L2 write path: 255 MB at 32 B/clk/SM is 28 us, and all 15 warps store at the
+//     same time.  Making every store a full 128-byte line (the second accumulator's lines are half-filled, the other half
+//     comes from the neighbouring warp) changes nothing: 125.9 vs 125.7 us with full-line stores to a wrong plane.
 
 // ------------------------------------------------------------------ tiled forward, pair-shared 64-bit operands ---
 // Measured on B200 (tools/lds_probe.cu): a warp-wide LDS.32 costs ~1.45 LSU cycles whatever its addresses, an LDS.64
