@@ -28,7 +28,7 @@ import torch.distributed as dist
 
 class UFlowTrainStep:
     def __init__(self, model, loss_fn, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, use_graph=True, world_size=1,
-                 n_buckets=4, global_census_norm=False, allreduce="auto", comm_ctas=16):
+                 n_buckets=4, global_census_norm=False, allreduce="auto", comm_ctas=32):
         dev0 = next(model.parameters()).device
         if allreduce == "auto":
             allreduce = "peer" if (world_size > 1 and dev0.type == "cuda") else "nccl"

@@ -74,6 +74,7 @@ def parse():
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "peer", "fused"],
                     help="gradient all-reduce of the multi-GPU step: the library's own NVLink kernel captured in the step "
                          "graph (fused), or NCCL between two graphs")
+    ap.add_argument("--comm-ctas", type=int, default=None, help="CTAs of an overlapped bucket all-reduce (peer mode; tuning)")
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager step between cudaProfilerStart/Stop (for `ncu --profile-from-start off`) and exit")
     return ap.parse_args()
@@ -519,8 +520,9 @@ def build_step(args, dev, world):
                                                    smooth_order=cfg["smooth_order"]))
         # N > 1: the census loss keeps the reference's batch-global normaliser (uflow_utils.py:293) through a 16-byte
         # peer all-reduce inside the captured step, so every N optimises the same loss as the single-process reference
+        extra = {"comm_ctas": args.comm_ctas} if args.comm_ctas else {}
         step = UFlowTrainStep(model, loss_fn, lr=1e-4, use_graph=not args.no_graph, world_size=world,
-                              allreduce=args.allreduce, global_census_norm=(world > 1 and args.allreduce != "nccl"))
+                              allreduce=args.allreduce, global_census_norm=(world > 1 and args.allreduce != "nccl"), **extra)
         import copy
         fresh = copy.deepcopy(model)      # in-situ kernel timings run on the initial weights, see main_b200
 
