@@ -24,6 +24,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O3",
     "-Xptxas", "-v",
 ]
+if os.environ.get("ARF_RELEASE") == "1":      # compile the test hooks of arf_debug_set out (csrc/common.cuh)
+    NVCC_FLAGS.append("-DARF_TEST_HOOKS=0")
 
 
 def _sources():

@@ -15,7 +15,7 @@
 #include "common.cuh"
 #include <math.h>
 
-thread_local int g_census_variant = 0;   // test hook, per calling thread (arf_debug_set key 5): 1 = force the per-pixel kernels, 8..64 = strip height
+ARF_HOOK g_census_variant = 0;   // test hook, per calling thread (arf_debug_set key 5): 1 = force the per-pixel kernels, 8..64 = strip height
 
 namespace {
 

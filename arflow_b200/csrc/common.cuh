@@ -42,6 +42,19 @@ static inline cudaError_t arf_ensure_smem(K kern, size_t bytes, std::atomic<unsi
         if (e__ != cudaSuccess) return (int)e__;                            \
     } while (0)
 
+// Kernel-selection / probe hooks of arf_debug_set (the parity tests force each kernel variant through them).  The in-tree
+// build keeps them (ARF_TEST_HOOKS=1); a release build compiles them out: `ARF_RELEASE=1 python -m arflow_b200.build`
+// passes -DARF_TEST_HOOKS=0, every hook becomes the constant 0, the variant branches fold away and arf_debug_set returns
+// ARF_EUNSUPPORTED.
+#ifndef ARF_TEST_HOOKS
+#define ARF_TEST_HOOKS 1
+#endif
+#if ARF_TEST_HOOKS
+#define ARF_HOOK thread_local int
+#else
+#define ARF_HOOK static constexpr int
+#endif
+
 #define ARF_REQUIRE(cond)                                    \
     do {                                                     \
         if (!(cond)) return ARF_EINVAL;                      \

@@ -803,9 +803,9 @@ int make_geom(CorrGeom& g, int B, int C, int H, int W, int pad, int ks, int md, 
 
 // Test hooks (arf_debug_set): per calling thread, so concurrent callers (one Python thread per GPU under the
 // reference's DataParallel) never see each other's settings; all default to 0 = production routing.
-thread_local int g_probe = 0;         // see corr_fwd_md4
-thread_local int g_variant = 0;       // kernel variant selection while tuning
-thread_local int g_force_no_tma = 0;  // exercise the cp.async producer on TMA-capable shapes
+ARF_HOOK g_probe = 0;         // see corr_fwd_md4
+ARF_HOOK g_variant = 0;       // kernel variant selection while tuning
+ARF_HOOK g_force_no_tma = 0;  // exercise the cp.async producer on TMA-capable shapes
 
 // The tiled kernels carry a fixed pipeline latency (forward ~11 us, backward ~35 us for any small problem) and, for
 // tensors TMA cannot describe (W % 4 != 0), a single-warp cp.async producer.  Measured with tools/microbench.py
@@ -825,11 +825,17 @@ inline bool is_fast(const CorrGeom& g, bool bwd) {
 
 }  // namespace
 
+#if ARF_TEST_HOOKS
 extern thread_local int g_warp_variant;   // warp.cu
 extern thread_local int g_trisolve_variant;   // stencil.cu
 extern thread_local int g_census_variant;     // census.cu
+#endif
 
 extern "C" int arf_debug_set(int key, int value) {
+#if !ARF_TEST_HOOKS
+    (void)key; (void)value;
+    return ARF_EUNSUPPORTED;
+#else
     if (key == 0) { g_force_no_tma = value; return ARF_OK; }
     if (key == 1) { g_variant = value; return ARF_OK; }
     if (key == 2) { g_probe = value; return ARF_OK; }
@@ -837,6 +843,7 @@ extern "C" int arf_debug_set(int key, int value) {
     if (key == 4) { g_trisolve_variant = value; return ARF_OK; }
     if (key == 5) { g_census_variant = value; return ARF_OK; }
     return ARF_EINVAL;
+#endif
 }
 
 extern "C" int arf_corr_out_dims(int H, int W, int pad, int ks, int md, int s1, int s2,

@@ -12,7 +12,7 @@
 //        wavefront on the sub-rectangle below/right of the start pixel and reduces the squares.
 #include "common.cuh"
 
-thread_local int g_trisolve_variant = 0;   // test hook, per calling thread (arf_debug_set key 4): 1 = force the wavefront solve
+ARF_HOOK g_trisolve_variant = 0;   // test hook, per calling thread (arf_debug_set key 4): 1 = force the wavefront solve
 
 namespace {
 

@@ -35,7 +35,7 @@
 //    output tile (fp32 shared atomics: 2.2 T/s) flushed with one reduction per touched element (~1.3-1.6).
 #include "common.cuh"
 
-thread_local int g_warp_variant = 0;   // test hook slot (arf_debug_set key 3), unused since the window kernels were removed
+ARF_HOOK g_warp_variant = 0;   // test hook slot (arf_debug_set key 3), unused since the window kernels were removed
 
 namespace {
 
