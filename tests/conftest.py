@@ -45,9 +45,24 @@ def rel_err(a, ref):
     return (a - ref).abs().max().item() / scale
 
 
-def assert_close(a, ref, rtol, what=""):
+def elementwise_err(a, ref):
+    """max over elements of |a - ref| / (|ref| + rms(ref)): a relative bound with an absolute floor, so that an error in a
+    small-magnitude region is not hidden behind the tensor's largest value."""
+    a = a.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    rms = ref.pow(2).mean().sqrt().item() if ref.numel() else 0.0
+    if rms == 0.0:
+        rms = 1.0
+    return ((a - ref).abs() / (ref.abs() + rms)).max().item() if ref.numel() else 0.0
+
+
+def assert_close(a, ref, rtol, what="", elementwise=True):
+    """Two bars: max|a-ref| / max|ref| <= rtol, and, element by element, |a-ref| <= 4 rtol (|ref| + rms(ref))."""
     e = rel_err(a, ref)
     assert e <= rtol, "%s: max|a-ref|/max|ref| = %.3e > %.1e" % (what, e, rtol)
+    if elementwise:
+        w = elementwise_err(a, ref)
+        assert w <= 4 * rtol, "%s: element-wise |a-ref|/(|ref|+rms) = %.3e > %.1e" % (what, w, 4 * rtol)
 
 
 @pytest.fixture(scope="session")
