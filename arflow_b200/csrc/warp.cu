@@ -243,8 +243,8 @@ warp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ field, fl
 // when the image alone cannot fill the machine, and the G partial flow gradients of a pixel are then summed through
 // shared memory in a fixed order (deterministic, no atomics on gfield).  Same address scheme as the forward.
 // kGx: also scatter the source gradient (red.global.add).
-template <int kCUB, bool kGx, int G>
-__global__ void __launch_bounds__(256)
+template <int kCUB, bool kGx, int G, int kMinB = 1>
+__global__ void __launch_bounds__(256, kMinB)
 warp_bwd_lean(const float* __restrict__ x, const float* __restrict__ field, const float* __restrict__ gy,
               float* __restrict__ gx, float* __restrict__ gfield, WarpGeom g, int ch_per_split) {
     constexpr int P = 256 / G;
@@ -440,17 +440,20 @@ extern "C" int arf_warp_bwd(const float* x, const float* field, const float* gy,
     while (G < 8 && G < want && 2 * G <= groups) G *= 2;
     const int ch_per_split = ((groups + G - 1) / G) * kCUB;
     dim3 grid(arf_cdiv((long long)Ho * Wo, 256 / G), 1, B);
-#define ARF_BWD_LEAN(CU, GX)                                                                                              \
+    // MINB = CTAs per SM the register allocation aims for.  The image warp (3 channels) is latency-bound - one round of
+    // flow loads, one of tap loads per thread - and gains from 5 CTAs of 48 registers (8x3x384x512: 29.7 -> 26.8 us;
+    // 6 or 8 CTAs spill: 30.8 / 40.9 us); the feature kernels keep their registers.
+#define ARF_BWD_LEAN(CU, GX, MINB)                                                                                        \
     do {                                                                                                                  \
-        if (G == 1) warp_bwd_lean<CU, GX, 1><<<grid, 256, 0, st>>>(x, field, gy, gx, gfield, g, ch_per_split);             \
-        else if (G == 2) warp_bwd_lean<CU, GX, 2><<<grid, 256, 0, st>>>(x, field, gy, gx, gfield, g, ch_per_split);        \
-        else if (G == 4) warp_bwd_lean<CU, GX, 4><<<grid, 256, 0, st>>>(x, field, gy, gx, gfield, g, ch_per_split);        \
-        else warp_bwd_lean<CU, GX, 8><<<grid, 256, 0, st>>>(x, field, gy, gx, gfield, g, ch_per_split);                    \
+        if (G == 1) warp_bwd_lean<CU, GX, 1, MINB><<<grid, 256, 0, st>>>(x, field, gy, gx, gfield, g, ch_per_split);       \
+        else if (G == 2) warp_bwd_lean<CU, GX, 2, MINB><<<grid, 256, 0, st>>>(x, field, gy, gx, gfield, g, ch_per_split);  \
+        else if (G == 4) warp_bwd_lean<CU, GX, 4, MINB><<<grid, 256, 0, st>>>(x, field, gy, gx, gfield, g, ch_per_split);  \
+        else warp_bwd_lean<CU, GX, 8, MINB><<<grid, 256, 0, st>>>(x, field, gy, gx, gfield, g, ch_per_split);              \
     } while (0)
-    if (gx) ARF_BWD_LEAN(4, true);
-    else if (kCUB == 3) ARF_BWD_LEAN(3, false);
-    else if (kCUB == 8) ARF_BWD_LEAN(8, false);
-    else ARF_BWD_LEAN(4, false);
+    if (gx) ARF_BWD_LEAN(4, true, 3);
+    else if (kCUB == 3) ARF_BWD_LEAN(3, false, 5);
+    else if (kCUB == 8) ARF_BWD_LEAN(8, false, 3);      // 80 registers; left alone ptxas takes 89 (2 CTAs): 24.7 vs 20.5 us
+    else ARF_BWD_LEAN(4, false, 4);
 #undef ARF_BWD_LEAN
     ARF_CHECK_LAUNCH();
     return ARF_OK;
