@@ -215,6 +215,26 @@ def test_ssim_and_resampler_golden():
     assert_close(gw, g["resampler_grad1_f64"], RTOL_GRAD)
 
 
+def test_census_loss_groups_equals_separate_calls():
+    """census_loss_groups on stacked inputs == one census_loss per batch slice, values and both gradients, bit for bit
+    (same kernels on views of the stacked tensors)."""
+    from arflow_b200 import uflow_utils as uu
+    gen = torch.Generator().manual_seed(9)
+    B, H, W = 2, 40, 72
+    a, b = torch.rand(2 * B, 3, H, W, generator=gen), torch.rand(2 * B, 3, H, W, generator=gen)
+    m = (torch.rand(2 * B, 1, H, W, generator=gen) > 0.3).float()
+    ac, bc = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    l = uu.census_loss_groups(ac, bc, m.cuda(), 2)
+    ga, gb = torch.autograd.grad(l[0] * 1.5 + l[1] * 0.5, [ac, bc])
+    for g, wgt in ((0, 1.5), (1, 0.5)):
+        sl = slice(g * B, (g + 1) * B)
+        a1, b1 = a[sl].cuda().requires_grad_(True), b[sl].cuda().requires_grad_(True)
+        l1 = uu.census_loss(a1, b1, m[sl].cuda())
+        g1a, g1b = torch.autograd.grad(l1 * wgt, [a1, b1])
+        assert torch.equal(l[g], l1)
+        assert torch.equal(ga[sl], g1a) and torch.equal(gb[sl], g1b)
+
+
 @pytest.mark.parametrize("C", [3, 8, 12, 40])
 def test_resampler_both_backward_kernels_vs_oracle(oracle, C):
     """arf_resampler_bwd owns a sample point by a thread (C <= 8) or by a warp (wider data); both against the float64
