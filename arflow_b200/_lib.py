@@ -36,6 +36,8 @@ PROTOTYPES = {
     "arf_census_num_partials": [c_int] * 3,
     "arf_census_fwd": [_P] * 6 + [c_int] * 4 + [c_float] * 3 + [_P],
     "arf_census_bwd": [_P] * 9 + [c_int] * 4 + [c_float] * 3 + [_P],
+    "arf_census_fwd_groups": [_P] * 6 + [c_int] * 5 + [c_float] * 3 + [_P],
+    "arf_census_bwd_groups": [_P] * 9 + [c_int] * 5 + [c_float] * 3 + [_P],
     "arf_smooth_num_partials": [c_int] * 3,
     "arf_smooth_fwd": [_P] * 4 + [c_int] * 8 + [c_float] * 3 + [_P],
     "arf_smooth_bwd": [_P] * 4 + [c_int] * 8 + [c_float] * 3 + [_P],

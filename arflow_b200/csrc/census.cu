@@ -250,7 +250,6 @@ census_fwd_sym(const float* __restrict__ im_a, const float* __restrict__ im_b, c
                long long nstrips, float scale, int want_sums, float eps, float q) {
     constexpr int TW = SymGeo<R>::kTW;
     __shared__ float ring[kSymWarps][2][kRing][TW];
-    __shared__ float red[2][kSymWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float (*ring_a)[TW] = ring[warp][0];
     float (*ring_b)[TW] = ring[warp][1];
@@ -348,27 +347,26 @@ census_fwd_sym(const float* __restrict__ im_a, const float* __restrict__ im_b, c
         }
     }
     if (want_sums) {
+        // one partial pair per STRIP (strips are ordered by batch item, so a group of the batch is a contiguous range)
         num = arf_warp_sum(num);
         den = arf_warp_sum(den);
-        if (lane == 0) { red[0][warp] = num; red[1][warp] = den; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float n = 0.f, d = 0.f;
-#pragma unroll
-            for (int w = 0; w < kSymWarps; ++w) { n += red[0][w]; d += red[1][w]; }
-            partials[2 * (size_t)blockIdx.x] = n;
-            partials[2 * (size_t)blockIdx.x + 1] = d;
+        const long long strip = (long long)blockIdx.x * kSymWarps + warp;
+        if (lane == 0 && strip < nstrips) {
+            partials[2 * (size_t)strip] = num;
+            partials[2 * (size_t)strip + 1] = den;
         }
     }
 }
 
-// out[0] = num, out[1] = den, out[2] = num / (den + 1e-6); fixed summation order (deterministic)
+// Block g: out[3g + {0,1,2}] = num, den, num / (den + 1e-6) of group g = partial entries [g * n, (g + 1) * n) (the partials
+// are ordered by batch item, a group is a contiguous range of the batch); fixed summation order (deterministic)
 __global__ void census_finalize_kernel(const float* __restrict__ partials, int n, float* __restrict__ out) {
     __shared__ double sn[256], sd[256];
+    const float* p = partials + 2 * (size_t)blockIdx.x * n;
     double a = 0.0, d = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) {
-        a += (double)partials[2 * (size_t)i];
-        d += (double)partials[2 * (size_t)i + 1];
+        a += (double)p[2 * (size_t)i];
+        d += (double)p[2 * (size_t)i + 1];
     }
     sn[threadIdx.x] = a;
     sd[threadIdx.x] = d;
@@ -382,9 +380,9 @@ __global__ void census_finalize_kernel(const float* __restrict__ partials, int n
     }
     if (threadIdx.x == 0) {
         float num = (float)sn[0], den = (float)sd[0];
-        out[0] = num;
-        out[1] = den;
-        out[2] = num / (den + 1e-6f);
+        out[3 * blockIdx.x + 0] = num;
+        out[3 * blockIdx.x + 1] = den;
+        out[3 * blockIdx.x + 2] = num / (den + 1e-6f);
     }
 }
 
@@ -411,7 +409,7 @@ __global__ void __launch_bounds__(kCThreads, 6)
 census_bwd_kernel(const float* __restrict__ im_a, const float* __restrict__ im_b, const float* __restrict__ ghamming,
                   const float* __restrict__ hamming, const float* __restrict__ mask, const float* __restrict__ sums,
                   const float* __restrict__ gloss, float* __restrict__ g_a, float* __restrict__ g_b, int B, int H,
-                  int W, int tiles_x, int tiles_y, float scale, float eps, float q) {
+                  int W, int tiles_x, int tiles_y, float scale, float eps, float q, int bg) {
     __shared__ float ga[kCTH + 2 * R][kCTW + 2 * R];
     __shared__ float gb[kCTH + 2 * R][kCTW + 2 * R];
     __shared__ float gh[kCTH + 2 * R][kCTW + 2 * R];   // upstream d(loss)/d(hamming), zero outside the image
@@ -422,9 +420,9 @@ census_bwd_kernel(const float* __restrict__ im_a, const float* __restrict__ im_b
     load_gray_tile<R>(gb, im_b, b, x0, y0, H, W);
     {
         float gl = 0.f, idn = 0.f;
-        if (!ghamming) {
-            gl = __ldg(gloss);
-            idn = 1.f / (__ldg(sums + 1) + 1e-6f);
+        if (!ghamming) {      // bg batch items per group: its own upstream gradient and normaliser
+            gl = __ldg(gloss + b / bg);
+            idn = 1.f / (__ldg(sums + 3 * (b / bg) + 1) + 1e-6f);
         }
         constexpr int TW = kCTW + 2 * R, THh = kCTH + 2 * R;
         for (int e = threadIdx.x; e < TW * THh; e += kCThreads) {
@@ -490,7 +488,7 @@ __global__ void __launch_bounds__(32 * kSymWarps)
 census_bwd_sym(const float* __restrict__ im_a, const float* __restrict__ im_b, const float* __restrict__ ghamming,
                const float* __restrict__ hamming, const float* __restrict__ mask, const float* __restrict__ sums,
                const float* __restrict__ gloss, float* __restrict__ g_a, float* __restrict__ g_b, int B, int H, int W,
-               int nsx, int nsy, int Hs, long long nstrips, float scale, float eps, float q) {
+               int nsx, int nsy, int Hs, long long nstrips, float scale, float eps, float q, int bg) {
     constexpr int TW = SymGeo<R>::kTW;
     __shared__ float ring[kSymWarps][3][kRing][TW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -506,9 +504,9 @@ census_bwd_sym(const float* __restrict__ im_a, const float* __restrict__ im_b, c
     const float* ib = im_b + (size_t)g.b * 3 * plane;
     const int xt0 = g.x_site0 - R;
     float gl = 0.f, idn = 0.f;
-    if (!ghamming) {
-        gl = __ldg(gloss);
-        idn = 1.f / (__ldg(sums + 1) + 1e-6f);
+    if (!ghamming) {          // bg batch items per group: its own upstream gradient and normaliser
+        gl = __ldg(gloss + g.b / bg);
+        idn = 1.f / (__ldg(sums + 3 * (g.b / bg) + 1) + 1e-6f);
     }
     // upstream gradient of one staged row: raw loads (clamped), finished by gh_store
     struct GhFetch { float h[3], m[3]; unsigned ok; };
@@ -667,9 +665,9 @@ inline int sym_strip_height(int B, int H, int W, int own_cols, int R, int reside
 
 extern "C" int arf_census_num_partials(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return ARF_EINVAL;
-    // upper bound over both kernel families: per-pixel tiles, and CTAs of the pair-symmetric strips at their smallest
+    // upper bound over both kernel families: per-pixel tiles, and the pair-symmetric strips at their smallest
     long long n = (long long)arf_cdiv(W, kCTW) * arf_cdiv(H, kCTH) * B;
-    long long m = ((long long)arf_cdiv(W, kSymCols - 6) * arf_cdiv(H, 8) * B + kSymWarps - 1) / kSymWarps;
+    long long m = (long long)arf_cdiv(W, kSymCols - 6) * arf_cdiv(H, 8) * B;
     if (m > n) n = m;
     return n > 0x7fffffffLL ? ARF_EINVAL : (int)n;
 }
@@ -683,7 +681,7 @@ inline bool use_sym(int B, int H, int W) {
 }
 template <int R>
 int launch_fwd_sym(const float* im_a, const float* im_b, const float* mask, float* hamming, float* partials, float* sums,
-                   int B, int H, int W, float scale, float eps, float q, cudaStream_t st) {
+                   int B, int H, int W, int groups, float scale, float eps, float q, cudaStream_t st) {
     const int hs = sym_strip_height(B, H, W, SymGeo<R>::kOwn, R, 4);
     const int nsx = arf_cdiv(W, SymGeo<R>::kOwn), nsy = arf_cdiv(H, hs);
     const long long nstrips = (long long)nsx * nsy * B;
@@ -693,15 +691,16 @@ int launch_fwd_sym(const float* im_a, const float* im_b, const float* mask, floa
                                                                   nstrips, scale, sums != nullptr, eps, q);
     ARF_CHECK_LAUNCH();
     if (sums) {
-        census_finalize_kernel<<<1, 256, 0, st>>>(partials, (int)nblk, sums);
+        if (nstrips / groups > 0x7fffffffLL) return ARF_EINVAL;
+        census_finalize_kernel<<<groups, 256, 0, st>>>(partials, (int)(nstrips / groups), sums);
         ARF_CHECK_LAUNCH();
     }
     return ARF_OK;
 }
 template <int R>
 int launch_bwd_sym(const float* im_a, const float* im_b, const float* ghamming, const float* hamming, const float* mask,
-                   const float* sums, const float* gloss, float* g_a, float* g_b, int B, int H, int W, float scale,
-                   float eps, float q, cudaStream_t st) {
+                   const float* sums, const float* gloss, float* g_a, float* g_b, int B, int H, int W, int groups,
+                   float scale, float eps, float q, cudaStream_t st) {
     const int hs = sym_strip_height(B, H, W, SymGeo<R>::kOwn, R, 3);
     const int nsx = arf_cdiv(W, SymGeo<R>::kOwn), nsy = arf_cdiv(H, hs);
     const long long nstrips = (long long)nsx * nsy * B;
@@ -711,7 +710,8 @@ int launch_bwd_sym(const float* im_a, const float* im_b, const float* ghamming, 
     do {                                                                                                               \
         census_bwd_sym<R, KA, KB><<<(unsigned)nblk, 32 * kSymWarps, 0, st>>>(im_a, im_b, ghamming, hamming, mask,    \
                                                                                sums, gloss, g_a, g_b, B, H, W, nsx,   \
-                                                                               nsy, hs, nstrips, scale, eps, q);       \
+                                                                               nsy, hs, nstrips, scale, eps, q,        \
+                                                                               B / groups);                            \
     } while (0)
     if (g_a && g_b) ARF_BWD_SYM(true, true);
     else if (g_b) ARF_BWD_SYM(false, true);
@@ -722,22 +722,22 @@ int launch_bwd_sym(const float* im_a, const float* im_b, const float* ghamming, 
 }
 }  // namespace
 
-extern "C" int arf_census_fwd(const float* im_a, const float* im_b, const float* mask, float* hamming,
-                              float* partials, float* sums, int B, int H, int W, int patch, float scale,
-                              float eps, float q, void* stream) {
+extern "C" int arf_census_fwd_groups(const float* im_a, const float* im_b, const float* mask, float* hamming,
+                                     float* partials, float* sums, int B, int H, int W, int groups, int patch,
+                                     float scale, float eps, float q, void* stream) {
     ARF_REQUIRE(im_a && im_b && hamming);
-    ARF_REQUIRE(B > 0 && H > 0 && W > 0 && patch >= 1 && (patch & 1));
+    ARF_REQUIRE(B > 0 && H > 0 && W > 0 && patch >= 1 && (patch & 1) && groups >= 1 && B % groups == 0);
     const int want = sums != nullptr;
     if (want) ARF_REQUIRE(partials != nullptr);
     const int tiles_x = arf_cdiv(W, kCTW), tiles_y = arf_cdiv(H, kCTH);
-    const int n = arf_census_num_partials(B, H, W);
-    if (n < 0) return n;
+    if (arf_census_num_partials(B, H, W) < 0) return ARF_EINVAL;
+    const int n = tiles_x * tiles_y * B;      // per-pixel kernels: one CTA (and one partial pair) per tile
     cudaStream_t st = (cudaStream_t)stream;
     if (use_sym(B, H, W)) {
         switch (patch / 2) {
-            case 1: return launch_fwd_sym<1>(im_a, im_b, mask, hamming, partials, sums, B, H, W, scale, eps, q, st);
-            case 2: return launch_fwd_sym<2>(im_a, im_b, mask, hamming, partials, sums, B, H, W, scale, eps, q, st);
-            case 3: return launch_fwd_sym<3>(im_a, im_b, mask, hamming, partials, sums, B, H, W, scale, eps, q, st);
+            case 1: return launch_fwd_sym<1>(im_a, im_b, mask, hamming, partials, sums, B, H, W, groups, scale, eps, q, st);
+            case 2: return launch_fwd_sym<2>(im_a, im_b, mask, hamming, partials, sums, B, H, W, groups, scale, eps, q, st);
+            case 3: return launch_fwd_sym<3>(im_a, im_b, mask, hamming, partials, sums, B, H, W, groups, scale, eps, q, st);
             default: return ARF_EUNSUPPORTED;
         }
     }
@@ -749,49 +749,64 @@ extern "C" int arf_census_fwd(const float* im_a, const float* im_b, const float*
     }
     ARF_CHECK_LAUNCH();
     if (want) {
-        census_finalize_kernel<<<1, 256, 0, st>>>(partials, n, sums);
+        census_finalize_kernel<<<groups, 256, 0, st>>>(partials, tiles_x * tiles_y * (B / groups), sums);
         ARF_CHECK_LAUNCH();
     }
+    return ARF_OK;
+}
+
+extern "C" int arf_census_fwd(const float* im_a, const float* im_b, const float* mask, float* hamming,
+                              float* partials, float* sums, int B, int H, int W, int patch, float scale,
+                              float eps, float q, void* stream) {
+    return arf_census_fwd_groups(im_a, im_b, mask, hamming, partials, sums, B, H, W, 1, patch, scale, eps, q, stream);
+}
+
+extern "C" int arf_census_bwd_groups(const float* im_a, const float* im_b, const float* ghamming, const float* hamming,
+                                     const float* mask, const float* sums, const float* gloss, float* g_a, float* g_b,
+                                     int B, int H, int W, int groups, int patch, float scale, float eps, float q,
+                                     void* stream) {
+    ARF_REQUIRE(im_a && im_b);
+    ARF_REQUIRE(ghamming || (hamming && sums && gloss));
+    ARF_REQUIRE(B > 0 && H > 0 && W > 0 && patch >= 1 && (patch & 1) && groups >= 1 && B % groups == 0);
+    if (!g_a && !g_b) return ARF_OK;
+    const int tiles_x = arf_cdiv(W, kCTW), tiles_y = arf_cdiv(H, kCTH);
+    if (arf_census_num_partials(B, H, W) < 0) return ARF_EINVAL;
+    const int n = tiles_x * tiles_y * B;
+    const int bg = B / groups;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (use_sym(B, H, W)) {
+        switch (patch / 2) {
+            case 1: return launch_bwd_sym<1>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, groups, scale, eps, q, st);
+            case 2: return launch_bwd_sym<2>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, groups, scale, eps, q, st);
+            case 3: return launch_bwd_sym<3>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, groups, scale, eps, q, st);
+            default: return ARF_EUNSUPPORTED;
+        }
+    }
+    switch (patch / 2) {
+        case 1:
+            if (g_a && g_b) census_bwd_kernel<1, true, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q, bg);
+            else if (g_b) census_bwd_kernel<1, false, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q, bg);
+            else census_bwd_kernel<1, true, false><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q, bg);
+            break;
+        case 2:
+            if (g_a && g_b) census_bwd_kernel<2, true, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q, bg);
+            else if (g_b) census_bwd_kernel<2, false, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q, bg);
+            else census_bwd_kernel<2, true, false><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q, bg);
+            break;
+        case 3:
+            if (g_a && g_b) census_bwd_kernel<3, true, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q, bg);
+            else if (g_b) census_bwd_kernel<3, false, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q, bg);
+            else census_bwd_kernel<3, true, false><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q, bg);
+            break;
+        default: return ARF_EUNSUPPORTED;
+    }
+    ARF_CHECK_LAUNCH();
     return ARF_OK;
 }
 
 extern "C" int arf_census_bwd(const float* im_a, const float* im_b, const float* ghamming, const float* hamming,
                               const float* mask, const float* sums, const float* gloss, float* g_a, float* g_b,
                               int B, int H, int W, int patch, float scale, float eps, float q, void* stream) {
-    ARF_REQUIRE(im_a && im_b);
-    ARF_REQUIRE(ghamming || (hamming && sums && gloss));
-    ARF_REQUIRE(B > 0 && H > 0 && W > 0 && patch >= 1 && (patch & 1));
-    if (!g_a && !g_b) return ARF_OK;
-    const int tiles_x = arf_cdiv(W, kCTW), tiles_y = arf_cdiv(H, kCTH);
-    const int n = arf_census_num_partials(B, H, W);
-    if (n < 0) return n;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (use_sym(B, H, W)) {
-        switch (patch / 2) {
-            case 1: return launch_bwd_sym<1>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, scale, eps, q, st);
-            case 2: return launch_bwd_sym<2>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, scale, eps, q, st);
-            case 3: return launch_bwd_sym<3>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, scale, eps, q, st);
-            default: return ARF_EUNSUPPORTED;
-        }
-    }
-    switch (patch / 2) {
-        case 1:
-            if (g_a && g_b) census_bwd_kernel<1, true, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
-            else if (g_b) census_bwd_kernel<1, false, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
-            else census_bwd_kernel<1, true, false><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
-            break;
-        case 2:
-            if (g_a && g_b) census_bwd_kernel<2, true, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
-            else if (g_b) census_bwd_kernel<2, false, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
-            else census_bwd_kernel<2, true, false><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
-            break;
-        case 3:
-            if (g_a && g_b) census_bwd_kernel<3, true, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
-            else if (g_b) census_bwd_kernel<3, false, true><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
-            else census_bwd_kernel<3, true, false><<<n, kCThreads, 0, st>>>(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, tiles_x, tiles_y, scale, eps, q);
-            break;
-        default: return ARF_EUNSUPPORTED;
-    }
-    ARF_CHECK_LAUNCH();
-    return ARF_OK;
+    return arf_census_bwd_groups(im_a, im_b, ghamming, hamming, mask, sums, gloss, g_a, g_b, B, H, W, 1, patch, scale, eps,
+                                 q, stream);
 }

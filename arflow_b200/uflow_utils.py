@@ -302,10 +302,8 @@ class _CensusLossFunction(torch.autograd.Function):
 
 class _CensusLossGroupsFunction(torch.autograd.Function):
     """census_loss for `groups` equally sized batch slices of stacked inputs (UFlowLoss runs its two directions stacked on
-    the batch): every slice is its own census_loss - own mask sum, own normaliser (uflow_utils.py:293) - evaluated by
-    the same kernels on views of the stacked tensors, and the backward writes each slice's gradient straight into its
-    part of ONE gradient tensor (slicing the inputs outside instead would cost a zero-fill and an add of full-size
-    gradients per slice).  Returns a (groups,) tensor of losses."""
+    the batch): every slice is its own census_loss - own mask sum, own normaliser (uflow_utils.py:293) - evaluated in ONE
+    launch each way (arf_census_*_groups), the backward writing ONE gradient tensor.  Returns a (groups,) tensor."""
 
     @staticmethod
     def forward(ctx, im_a, im_b, mask, groups, patch, eps, q):
@@ -313,46 +311,36 @@ class _CensusLossGroupsFunction(torch.autograd.Function):
         if im_a.shape != im_b.shape or im_a.dim() != 4 or im_a.shape[1] != 3 or im_a.shape[0] % groups != 0:
             raise ValueError("census_loss: expected two (groups*B,3,H,W) images of equal shape")
         N, _, H, W = im_a.shape
-        B = N // groups
         mask = mask.detach().contiguous()
         if mask.shape != (N, 1, H, W):
             raise ValueError("census_loss: mask must be (groups*B,1,H,W)")
         lib = _lib.load()
         with torch.cuda.device_of(im_a):
             ham = _new_like(im_a, (N, 1, H, W))
-            partials = _new_like(im_a, (2 * lib.arf_census_num_partials(B, H, W),))
-            sums = []
-            for g in range(groups):
-                sl = slice(g * B, (g + 1) * B)
-                sg = _new_like(im_a, (3,))
-                _lib.call("arf_census_fwd", _lib.dev_ptr(im_a[sl], "image_a"), _lib.dev_ptr(im_b[sl], "image_b"),
-                          _lib.dev_ptr(mask[sl], "mask"), _lib.dev_ptr(ham[sl]), _lib.dev_ptr(partials), _lib.dev_ptr(sg),
-                          B, H, W, patch, 1.0, float(eps), float(q), _lib.stream_ptr())
-                if _census_group is not None:
-                    sg = globalise_census_sums(sg, _census_group)
-                sums.append(sg)
-        ctx.save_for_backward(im_a, im_b, mask, ham, *sums)
+            partials = _new_like(im_a, (2 * lib.arf_census_num_partials(N, H, W),))
+            sums = _new_like(im_a, (3 * groups,))
+            _lib.call("arf_census_fwd_groups", _lib.dev_ptr(im_a, "image_a"), _lib.dev_ptr(im_b, "image_b"),
+                      _lib.dev_ptr(mask, "mask"), _lib.dev_ptr(ham), _lib.dev_ptr(partials), _lib.dev_ptr(sums),
+                      N, H, W, groups, patch, 1.0, float(eps), float(q), _lib.stream_ptr())
+        if _census_group is not None:
+            sums = torch.cat([globalise_census_sums(sums[3 * g:3 * g + 3], _census_group) for g in range(groups)])
+        ctx.save_for_backward(im_a, im_b, mask, ham, sums)
         ctx.cfg = (groups, patch, float(eps), float(q))
-        return torch.stack([sg[2] for sg in sums])
+        return sums[2::3].clone()
 
     @staticmethod
     def backward(ctx, gloss):
-        im_a, im_b, mask, ham = ctx.saved_tensors[:4]
-        sums = ctx.saved_tensors[4:]
+        im_a, im_b, mask, ham, sums = ctx.saved_tensors
         groups, patch, eps, q = ctx.cfg
         N, _, H, W = im_a.shape
-        B = N // groups
         gloss = gloss.contiguous()
         with torch.cuda.device_of(im_a):
             ga = torch.empty_like(im_a) if ctx.needs_input_grad[0] else None
             gb = torch.empty_like(im_b) if ctx.needs_input_grad[1] else None
-            for g in range(groups):
-                sl = slice(g * B, (g + 1) * B)
-                _lib.call("arf_census_bwd", _lib.dev_ptr(im_a[sl]), _lib.dev_ptr(im_b[sl]), None, _lib.dev_ptr(ham[sl]),
-                          _lib.dev_ptr(mask[sl]), _lib.dev_ptr(sums[g]), _lib.dev_ptr(gloss[g:g + 1], "grad"),
-                          _lib.dev_ptr(ga[sl] if ga is not None else None, allow_none=True),
-                          _lib.dev_ptr(gb[sl] if gb is not None else None, allow_none=True),
-                          B, H, W, patch, 1.0, eps, q, _lib.stream_ptr())
+            _lib.call("arf_census_bwd_groups", _lib.dev_ptr(im_a), _lib.dev_ptr(im_b), None, _lib.dev_ptr(ham),
+                      _lib.dev_ptr(mask), _lib.dev_ptr(sums), _lib.dev_ptr(gloss, "grad"),
+                      _lib.dev_ptr(ga, allow_none=True), _lib.dev_ptr(gb, allow_none=True),
+                      N, H, W, groups, patch, 1.0, eps, q, _lib.stream_ptr())
         return ga, gb, None, None, None, None, None
 
 

@@ -151,6 +151,7 @@ class ClockSampler:
 # SURVEY §8(a) entry points: the only candidates for `roofline` (conv glue such as arf_bias_leaky_* / arf_nhwc_* is
 # timed and listed under `kernels`, but it is not the hot path the metric names).
 HOTPATH = ("arf_corr_fwd", "arf_corr_bwd", "arf_warp_fwd", "arf_warp_bwd", "arf_census_fwd", "arf_census_bwd",
+           "arf_census_fwd_groups", "arf_census_bwd_groups",
            "arf_smooth_fwd", "arf_smooth_bwd", "arf_range_map", "arf_range_map_bwd", "arf_inside_mask",
            "arf_count_to_mask", "arf_occ_bidir", "arf_stencil_mv_fwd", "arf_stencil_mv_bwd", "arf_trisolve",
            "arf_ssim_fwd", "arf_ssim_bwd", "arf_featnorm_fwd", "arf_featnorm_bwd", "arf_resize_bilinear_fwd",
@@ -173,10 +174,10 @@ def alg_bytes(name, a):
     if name == "arf_warp_bwd":
         B, C, _, _, Ho, Wo = a[5:11]
         return B * Ho * Wo * ((12 if a[3] else 8) * C + 16)
-    if name == "arf_census_fwd":
+    if name in ("arf_census_fwd", "arf_census_fwd_groups"):
         B, Hh, Ww = a[6:9]
         return B * Hh * Ww * 32
-    if name == "arf_census_bwd":
+    if name in ("arf_census_bwd", "arf_census_bwd_groups"):
         B, Hh, Ww = a[9:12]
         return B * Hh * Ww * (24 + 8 + 12 * ((a[7] is not None) + (a[8] is not None)))
     if name in ("arf_resize_bilinear_fwd", "arf_resize_bilinear_bwd"):
@@ -244,12 +245,14 @@ def alg_work(name, a):
     if name == "arf_warp_bwd":
         B, C, _, _, Ho, Wo = a[5:11]
         return "B%d C%d %dx%d%s" % (B, C, Ho, Wo, "" if a[3] else " flow-grad only"), B * Ho * Wo * C * 16, 0
-    if name == "arf_census_fwd":
-        B, Hh, Ww, patch = a[6:10]
+    if name in ("arf_census_fwd", "arf_census_fwd_groups"):
+        B, Hh, Ww = a[6:9]
+        patch = a[9] if name == "arf_census_fwd" else a[10]
         n = patch * patch - 1
         return "B%d %dx%d p%d" % (B, Hh, Ww, patch), B * Hh * Ww * 7 * n, int(B * Hh * Ww * CENSUS_MUFU_FWD * n)
-    if name == "arf_census_bwd":
-        B, Hh, Ww, patch = a[9:13]
+    if name in ("arf_census_bwd", "arf_census_bwd_groups"):
+        B, Hh, Ww = a[9:12]
+        patch = a[12] if name == "arf_census_bwd" else a[13]
         n = patch * patch - 1
         return "B%d %dx%d p%d" % (B, Hh, Ww, patch), B * Hh * Ww * 22 * n, int(B * Hh * Ww * CENSUS_MUFU_BWD * n)
     if name in ("arf_resize_bilinear_fwd", "arf_resize_bilinear_bwd"):
@@ -374,15 +377,16 @@ def hotpath_rooflines(B2, C, h, w, Bimg, H, W, pk):
             m = torch.rand(Bimg, 1, H, W, device="cuda")
             ham = torch.empty(Bimg, 1, H, W, device="cuda")
             part = torch.empty(2 * npart, device="cuda")
-            sums, gl = torch.ones(3, device="cuda"), torch.ones(1, device="cuda")
+            ng = 2 if Bimg % 2 == 0 else 1
+            sums, gl = torch.ones(3 * ng, device="cuda"), torch.ones(ng, device="cuda")
             gb = torch.empty_like(b)
             if kind == "fwd":
-                return lambda: lib.arf_census_fwd(a.data_ptr(), b.data_ptr(), m.data_ptr(), ham.data_ptr(), part.data_ptr(),
-                                                  sums.data_ptr(), Bimg, H, W, 7, 1.0, 0.01, 0.4, cs())
-            lib.arf_census_fwd(a.data_ptr(), b.data_ptr(), m.data_ptr(), ham.data_ptr(), part.data_ptr(), sums.data_ptr(),
-                               Bimg, H, W, 7, 1.0, 0.01, 0.4, cs())
-            return lambda: lib.arf_census_bwd(a.data_ptr(), b.data_ptr(), None, ham.data_ptr(), m.data_ptr(), sums.data_ptr(),
-                                              gl.data_ptr(), None, gb.data_ptr(), Bimg, H, W, 7, 1.0, 0.01, 0.4, cs())
+                return lambda: lib.arf_census_fwd_groups(a.data_ptr(), b.data_ptr(), m.data_ptr(), ham.data_ptr(), part.data_ptr(),
+                                                         sums.data_ptr(), Bimg, H, W, ng, 7, 1.0, 0.01, 0.4, cs())
+            lib.arf_census_fwd_groups(a.data_ptr(), b.data_ptr(), m.data_ptr(), ham.data_ptr(), part.data_ptr(), sums.data_ptr(),
+                                      Bimg, H, W, ng, 7, 1.0, 0.01, 0.4, cs())
+            return lambda: lib.arf_census_bwd_groups(a.data_ptr(), b.data_ptr(), None, ham.data_ptr(), m.data_ptr(), sums.data_ptr(),
+                                                     gl.data_ptr(), None, gb.data_ptr(), Bimg, H, W, ng, 7, 1.0, 0.01, 0.4, cs())
         return make
     labc = "B%d %dx%d p7" % (Bimg, H, W)
     add("arf_census_fwd", labc, pxi * 32, pxi * 7 * 48, int(pxi * CENSUS_MUFU_FWD * 48), mk_c("fwd"))
@@ -853,7 +857,9 @@ def main_b200(args):
             # finest-level shapes of this configuration: both directions stacked on the batch for the feature-level
             # kernels (one direction in config 1), census per direction (n_samples * B in the ELBO loss)
             b_feat = B if args.config == 1 else 2 * B
-            b_img = 4 * B if args.config == 3 else B
+            # census: UFlowLoss stacks its two directions (2B images, two normaliser groups); the ELBO loss evaluates
+            # n_samples * B images per direction
+            b_img = 4 * B if args.config == 3 else (2 * B if args.config in (2, 4) else B)
             hot, _ = hotpath_rooflines(b_feat, 32, H // 4, W // 4, b_img, H, W, pk)
 
     # ---- CPU baseline (rank 0, N=1 only) ----

@@ -151,6 +151,17 @@ int arf_census_bwd(const float* im_a, const float* im_b, const float* ghamming, 
                    const float* mask, const float* sums, const float* gloss, float* g_a, float* g_b,
                    int B, int H, int W, int patch, float scale, float eps, float q, void* stream);
 
+/* The same for `groups` equally sized, consecutive slices of the batch in ONE launch each way (B % groups == 0): every
+ * slice is its own census_loss - own mask sum and normaliser (uflow_utils.py:293) - with sums[3g + {0,1,2}] and
+ * gloss[g] for slice g.  UFlowLoss (losses/uflow_loss.py:28-54) evaluates its two directions this way, stacked on the
+ * batch.  arf_census_fwd / arf_census_bwd are the groups = 1 case. */
+int arf_census_fwd_groups(const float* im_a, const float* im_b, const float* mask, float* hamming,
+                          float* partials, float* sums, int B, int H, int W, int groups, int patch, float scale,
+                          float eps, float q, void* stream);
+int arf_census_bwd_groups(const float* im_a, const float* im_b, const float* ghamming, const float* hamming,
+                          const float* mask, const float* sums, const float* gloss, float* g_a, float* g_b,
+                          int B, int H, int W, int groups, int patch, float scale, float eps, float q, void* stream);
+
 /* ---------------------------------------------------------------- smoothness ----------- */
 int arf_smooth_num_partials(int B, int H, int W);
 

@@ -215,12 +215,13 @@ def test_ssim_and_resampler_golden():
     assert_close(gw, g["resampler_grad1_f64"], RTOL_GRAD)
 
 
-def test_census_loss_groups_equals_separate_calls():
-    """census_loss_groups on stacked inputs == one census_loss per batch slice, values and both gradients, bit for bit
-    (same kernels on views of the stacked tensors)."""
+@pytest.mark.parametrize("small", [True, False])
+def test_census_loss_groups_equals_separate_calls(small):
+    """census_loss_groups on stacked inputs (one launch for both slices) == one census_loss per batch slice: the per-pixel
+    arithmetic is the same, only the order of the partial sums of the normaliser differs (double accumulation)."""
     from arflow_b200 import uflow_utils as uu
     gen = torch.Generator().manual_seed(9)
-    B, H, W = 2, 40, 72
+    B, H, W = (2, 40, 72) if small else (4, 128, 160)     # per-pixel kernels / pair-symmetric strip kernels
     a, b = torch.rand(2 * B, 3, H, W, generator=gen), torch.rand(2 * B, 3, H, W, generator=gen)
     m = (torch.rand(2 * B, 1, H, W, generator=gen) > 0.3).float()
     ac, bc = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
@@ -231,8 +232,9 @@ def test_census_loss_groups_equals_separate_calls():
         a1, b1 = a[sl].cuda().requires_grad_(True), b[sl].cuda().requires_grad_(True)
         l1 = uu.census_loss(a1, b1, m[sl].cuda())
         g1a, g1b = torch.autograd.grad(l1 * wgt, [a1, b1])
-        assert torch.equal(l[g], l1)
-        assert torch.equal(ga[sl], g1a) and torch.equal(gb[sl], g1b)
+        assert_close(l[g], l1, 1e-6, "loss of slice %d" % g)
+        assert_close(ga[sl], g1a, 1e-6, "d/d image_a")
+        assert_close(gb[sl], g1b, 1e-6, "d/d image_b")
 
 
 @pytest.mark.parametrize("C", [3, 8, 12, 40])
