@@ -29,6 +29,8 @@ prof corr_bwd_cfg2 corr_bwd_md4 corr_bwd --shapes 16x32x96x128
 prof warp_fwd warp_fwd_kernel warp --flow smooth --shapes 16x32x96x128
 prof warp_bwd_gx warp_bwd_lean warp --flow smooth --shapes 16x32x96x128
 prof census_fwd census_fwd_sym census --shapes 8x3x384x512
+prof census_fwd_b16 census_fwd_sym census --shapes 16x3x384x512
+prof census_bwd_b16 census_bwd_sym census --shapes 16x3x384x512
 prof census_bwd census_bwd_sym census --shapes 8x3x384x512
 fi
 prof stencil_fwd 'stencil_mv_kernel' stencil
