@@ -559,9 +559,11 @@ corr_fwd_md4_p2(const __grid_constant__ CUtensorMap map1, const __grid_constant_
 // sit in registers next to the accumulators, which leaves 8 channels per warp (0.29 LDS per FMA, -16 %) at 10 warps.
 constexpr int kBCg = 8;                  // channels per warp
 
-template <int RG, int CG, int STG>
+// RT = rows per warp: 8 (72 + 8 x 16 LDS per 576 FMAs and dx step) for the big items, 4 for the small-problem items (more
+// LDS per FMA, but half the latency of an item and twice as many items to spread over the SMs)
+template <int RG, int CG, int STG, int RT = kTH>
 struct BwdCfg {
-    static constexpr int kTileH = kTH * RG;           // tile height
+    static constexpr int kTileH = RT * RG;            // tile height
     static constexpr int kHaloH = kTileH + 2 * kMD;
     static constexpr int kC = kBCg * CG;              // channels per work item
     static constexpr int kConsumers = RG * CG;
@@ -569,9 +571,9 @@ struct BwdCfg {
     static constexpr int kStages = STG;               // slab ring depth
 };
 
-template <bool kSecond, int RG, int CG, int STG>
+template <bool kSecond, int RG, int CG, int STG, int RT = kTH>
 struct BwdSmem {
-    using Cfg = BwdCfg<RG, CG, STG>;
+    using Cfg = BwdCfg<RG, CG, STG, RT>;
     // The second gradient reads gO at (y-dy, x-dx): its slab carries the 4-px halo in both directions.
     // (A tiled TMA load needs a 16-byte aligned innermost coordinate — measured: x0-3 raises "illegal
     // instruction" — so the horizontal shift is applied when reading, not when loading.)
@@ -582,13 +584,14 @@ struct BwdSmem {
     uint64_t f_full[CG], f_empty, s_full[STG], s_empty[STG];
 };
 
-template <bool kSecond, bool kTma, int RG, int CG, int STG>
+template <bool kSecond, bool kTma, int RG, int CG, int STG, int RT = kTH>
 __device__ __forceinline__ void corr_bwd_body(unsigned char* smem_raw, const CUtensorMap* mapF, const CUtensorMap* mapG,
                                               const float* __restrict__ Fsrc, const float* __restrict__ gout,
                                               float* __restrict__ gin, int B, int C, int H, int W, int tiles_x,
                                               int tiles_y, int nsuper, float inv_c) {
-    using Cfg = BwdCfg<RG, CG, STG>;
-    using Smem = BwdSmem<kSecond, RG, CG, STG>;
+    using Cfg = BwdCfg<RG, CG, STG, RT>;
+    using Smem = BwdSmem<kSecond, RG, CG, STG, RT>;
+    constexpr int kTH = RT, kHH = RT + 2 * kMD;      // shadow the forward kernel's 8-row constants
     constexpr int kSlabRows = Smem::kSlabRows;
     constexpr int kSlabW = Smem::kSlabW;
     constexpr int kBTH = Cfg::kTileH, kBHH = Cfg::kHaloH, kBC = Cfg::kC, kBConsumers = Cfg::kConsumers;
@@ -736,24 +739,24 @@ __device__ __forceinline__ void corr_bwd_body(unsigned char* smem_raw, const CUt
 struct BwdMaps { CUtensorMap m[4]; };
 
 // blockIdx.y + y_base: 0 = gradient w.r.t. f1, 1 = gradient w.r.t. f2
-template <bool kTma, int RG, int CG, int STG>
-__global__ void __launch_bounds__((BwdCfg<RG, CG, STG>::kThreads), 1)
+template <bool kTma, int RG, int CG, int STG, int RT = kTH, int kMinB = 1>
+__global__ void __launch_bounds__((BwdCfg<RG, CG, STG, RT>::kThreads), kMinB)
 corr_bwd_md4(const __grid_constant__ BwdMaps maps, const float* __restrict__ f1, const float* __restrict__ f2,
              const float* __restrict__ gout, float* __restrict__ g1, float* __restrict__ g2, int y_base, int B, int C,
              int H, int W, int tiles_x, int tiles_y, int nsuper, float inv_c) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     if (blockIdx.y + y_base == 0)
-        corr_bwd_body<false, kTma, RG, CG, STG>(smem_raw, &maps.m[0], &maps.m[1], f2, gout, g1, B, C, H, W, tiles_x, tiles_y,
+        corr_bwd_body<false, kTma, RG, CG, STG, RT>(smem_raw, &maps.m[0], &maps.m[1], f2, gout, g1, B, C, H, W, tiles_x, tiles_y,
                                                 nsuper, inv_c);
     else
-        corr_bwd_body<true, kTma, RG, CG, STG>(smem_raw, &maps.m[2], &maps.m[3], f1, gout, g2, B, C, H, W, tiles_x, tiles_y,
+        corr_bwd_body<true, kTma, RG, CG, STG, RT>(smem_raw, &maps.m[2], &maps.m[3], f1, gout, g2, B, C, H, W, tiles_x, tiles_y,
                                                nsuper, inv_c);
 }
 
-template <int RG, int CG, int STG>
+template <int RG, int CG, int STG, int RT = kTH, int kMinB = 1>
 int launch_bwd_md4(const float* f1, const float* f2, const float* gout, float* g1, float* g2, int B, int C, int H, int W,
                    bool want_tma, int ctas_per_sm, cudaStream_t st) {
-    using Cfg = BwdCfg<RG, CG, STG>;
+    using Cfg = BwdCfg<RG, CG, STG, RT>;
     const int tiles_x = arf_cdiv(W, kTW), tiles_y = arf_cdiv(H, Cfg::kTileH), nsuper = arf_cdiv(C, Cfg::kC);
     const long long nitems = (long long)tiles_x * tiles_y * B * nsuper;
     const long long cap = (long long)ARF_NUM_SMS * ctas_per_sm;
@@ -771,15 +774,15 @@ int launch_bwd_md4(const float* f1, const float* f2, const float* gout, float* g
         tma = arf::make_map_nchw(&maps.m[2], f1, B, C, H, W, kHW, Cfg::kHaloH, kBCg) &&
               arf::make_map_costvol(&maps.m[3], gout, B, kD, H, W, kHW, Cfg::kHaloH);
     const float inv_c = 1.0f / (float)C;
-    const size_t smem = g2 ? sizeof(BwdSmem<true, RG, CG, STG>) : sizeof(BwdSmem<false, RG, CG, STG>);
+    const size_t smem = g2 ? sizeof(BwdSmem<true, RG, CG, STG, RT>) : sizeof(BwdSmem<false, RG, CG, STG, RT>);
     const int y_base = g1 ? 0 : 1;
     if (tma) {
-        ARF_ENSURE_SMEM((corr_bwd_md4<true, RG, CG, STG>), sizeof(BwdSmem<true, RG, CG, STG>));
-        corr_bwd_md4<true, RG, CG, STG><<<grid, Cfg::kThreads, smem, st>>>(maps, f1, f2, gout, g1, g2, y_base, B, C, H, W,
+        ARF_ENSURE_SMEM((corr_bwd_md4<true, RG, CG, STG, RT, kMinB>), sizeof(BwdSmem<true, RG, CG, STG, RT>));
+        corr_bwd_md4<true, RG, CG, STG, RT, kMinB><<<grid, Cfg::kThreads, smem, st>>>(maps, f1, f2, gout, g1, g2, y_base, B, C, H, W,
                                                                           tiles_x, tiles_y, nsuper, inv_c);
     } else {
-        ARF_ENSURE_SMEM((corr_bwd_md4<false, RG, CG, STG>), sizeof(BwdSmem<true, RG, CG, STG>));
-        corr_bwd_md4<false, RG, CG, STG><<<grid, Cfg::kThreads, smem, st>>>(maps, f1, f2, gout, g1, g2, y_base, B, C, H, W,
+        ARF_ENSURE_SMEM((corr_bwd_md4<false, RG, CG, STG, RT, kMinB>), sizeof(BwdSmem<true, RG, CG, STG, RT>));
+        corr_bwd_md4<false, RG, CG, STG, RT, kMinB><<<grid, Cfg::kThreads, smem, st>>>(maps, f1, f2, gout, g1, g2, y_base, B, C, H, W,
                                                                            tiles_x, tiles_y, nsuper, inv_c);
     }
     ARF_CHECK_LAUNCH();
@@ -951,26 +954,36 @@ extern "C" int arf_corr_bwd(const float* f1, const float* f2, const float* gout,
     cudaStream_t st = (cudaStream_t)stream;
     if (is_fast(g, true)) {
         if (!g1 && !g2) return ARF_OK;
-        // Three item shapes; a launch takes ceil(items / resident CTAs) rounds of roughly constant duration, so the shape
-        // is chosen by rounds x measured round time (B200, tools/microbench.py corr_bwd --variant 10|11|12, both gradients):
-        //   0: <2,4> 32x16 px x 32 ch, 1 CTA/SM, ~16 us    1: <2,2> 32x16 px x 16 ch, 1 CTA/SM, ~11 us
+        // Six item shapes; a launch takes ceil(items / resident CTAs) rounds of roughly constant duration, so the shape is
+        // chosen by rounds x measured round time (B200, tools/microbench.py corr_bwd --variant 10..15, both gradients):
+        //   0: <2,4> 32x16 px x 32 ch, 8 rows per warp, 1 CTA/SM, ~16 us     1: <2,2> 32x16 px x 16 ch, 1 CTA/SM, ~11 us
         //   2: <1,4> 32x8 px x 32 ch, 2 CTAs/SM, ~22 us for a full pair
-        // e.g. 16x32x24x32: 18.5 / 13.1 / 12.9 us, 16x96x24x32: 33 / 33 / 26, 16x64x48x64: 50 / 62 / 64, 1x32x96x160: 18 / 13 / 14.
-        // (8-channel items, <2,1> and <1,1>, re-stream the gO slabs four times as often and lose everywhere: 65 / 68 us at
-        // 16x32x48x64 against 33.)
+        // and with 4 rows per warp (more LDS per FMA, but short items for the levels that cannot fill the machine):
+        //   3: <1,4> 32x4 px x 32 ch, 2 CTAs/SM, ~10 us    4: <3,4> 32x12 px x 32 ch, 1 CTA/SM, ~13.5 us    5: <2,4> 32x8, ~10.3 us
+        // e.g. 16x32x48x64: 34 / 41 / 44 / 30 / 29 / 30 us, 16x32x12x16: 13 / 13 / 13 / 8.7, 16x96x24x32: 33 / 33 / 26 / 21 /
+        // 28 / 21, 16x32x96x128: 95 (0) vs 92.5 (4), 64x32x96x128: 321 (0) vs 357 (4).  (8-channel items re-stream the gO slabs
+        // four times as often and lose everywhere: 65 / 68 us at 16x32x48x64.)
         const int ngrad = (g1 ? 1 : 0) + (g2 ? 1 : 0);
         const long long tx = arf_cdiv(W, kTW), sms = ARF_NUM_SMS;
-        const long long n0 = tx * arf_cdiv(H, 2 * kTH) * B * arf_cdiv(C, 32) * ngrad;
-        const long long n1 = tx * arf_cdiv(H, 2 * kTH) * B * arf_cdiv(C, 16) * ngrad;
-        const long long n2 = tx * arf_cdiv(H, kTH) * B * arf_cdiv(C, 32) * ngrad;
-        const long long c0 = ((n0 + sms - 1) / sms) * 16, c1 = ((n1 + sms - 1) / sms) * 11, c2 = ((n2 + 2 * sms - 1) / (2 * sms)) * 22;
-        int cfg = (c0 <= c1 && c0 <= c2) ? 0 : (c1 <= c2 ? 1 : 2);
-        if (g_variant >= 10 && g_variant <= 12) cfg = g_variant - 10;   // tuning hook
+        const long long c32 = arf_cdiv(C, 32), c16 = arf_cdiv(C, 16);
+        const long long n[6] = {tx * arf_cdiv(H, 16) * B * c32 * ngrad, tx * arf_cdiv(H, 16) * B * c16 * ngrad,
+                                tx * arf_cdiv(H, 8) * B * c32 * ngrad,  tx * arf_cdiv(H, 4) * B * c32 * ngrad,
+                                tx * arf_cdiv(H, 12) * B * c32 * ngrad, tx * arf_cdiv(H, 8) * B * c32 * ngrad};
+        const double t[6] = {(double)((n[0] + sms - 1) / sms) * 16.0,          (double)((n[1] + sms - 1) / sms) * 11.0,
+                             (double)((n[2] + 2 * sms - 1) / (2 * sms)) * 22.0, (double)((n[3] + 2 * sms - 1) / (2 * sms)) * 10.0,
+                             (double)((n[4] + sms - 1) / sms) * 13.5,          (double)((n[5] + sms - 1) / sms) * 10.3};
+        int cfg = 0;
+        for (int k = 1; k < 6; ++k)
+            if (t[k] < t[cfg]) cfg = k;
+        if (g_variant >= 10 && g_variant <= 15) cfg = g_variant - 10;   // tuning hook
         const bool tma = !g_force_no_tma;
         switch (cfg) {
             case 0: return launch_bwd_md4<2, 4, 3>(f1, f2, gout, g1, g2, B, C, H, W, tma, 1, st);
             case 1: return launch_bwd_md4<2, 2, 2>(f1, f2, gout, g1, g2, B, C, H, W, tma, 1, st);
-            default: return launch_bwd_md4<1, 4, 3>(f1, f2, gout, g1, g2, B, C, H, W, tma, 2, st);
+            case 2: return launch_bwd_md4<1, 4, 3>(f1, f2, gout, g1, g2, B, C, H, W, tma, 2, st);
+            case 3: return launch_bwd_md4<1, 4, 2, 4, 2>(f1, f2, gout, g1, g2, B, C, H, W, tma, 2, st);
+            case 4: return launch_bwd_md4<3, 4, 3, 4, 1>(f1, f2, gout, g1, g2, B, C, H, W, tma, 1, st);
+            default: return launch_bwd_md4<2, 4, 2, 4, 1>(f1, f2, gout, g1, g2, B, C, H, W, tma, 1, st);
         }
     }
     long long total = (long long)B * C * H * W;

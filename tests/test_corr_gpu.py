@@ -125,6 +125,29 @@ def test_both_tiled_forward_kernels_vs_oracle(oracle, shape):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 24, 32), (3, 20, 50, 68), (1, 64, 13, 36), (2, 40, 12, 16)])
+def test_all_tiled_backward_item_shapes_vs_oracle(oracle, shape):
+    """arf_corr_bwd picks one of six work-item shapes by a cost model; the debug hook forces each.  All must match the C
+    oracle and each other bit for bit (the per-element order of the fused multiply-adds does not depend on the item)."""
+    from arflow_b200 import _lib
+    gen = torch.Generator().manual_seed(sum(shape))
+    f1, f2 = torch.randn(shape, generator=gen), torch.randn(shape, generator=gen)
+    w = torch.randn(shape[0], 81, shape[2], shape[3], generator=gen)
+    r1, r2 = oracle.corr_bwd_c(f1, f2, w)
+    res = []
+    for variant in (10, 11, 12, 13, 14, 15):
+        _lib.call("arf_debug_set", 1, variant)
+        try:
+            _, g1, g2 = _run(f1, f2, w, pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1)
+        finally:
+            _lib.call("arf_debug_set", 1, 0)
+        assert_close(g1, r1, RTOL_GRAD, "grad f1, item shape %d" % variant)
+        assert_close(g2, r2, RTOL_GRAD, "grad f2, item shape %d" % variant)
+        res.append((g1, g2))
+    for g1, g2 in res[1:]:
+        assert torch.equal(g1, res[0][0]) and torch.equal(g2, res[0][1])
+
+
 # Full BASELINE sizes against the C oracle (double accumulation): config 2's finest level, and batch 16 at the
 # channel counts / pyramid levels of the PWC-Lite family (models/pwclite.py:113: C = 64, 96, 128, 192 at 1/8 .. 1/64
 # of 384x512) plus config 1's own level shapes (SURVEY §8d).

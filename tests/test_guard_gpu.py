@@ -48,7 +48,7 @@ CORR_SHAPES = [(2, 32, 24, 32), (1, 20, 13, 36), (3, 7, 33, 65), (1, 192, 6, 10)
 
 
 @pytest.mark.parametrize("shape", CORR_SHAPES)
-@pytest.mark.parametrize("variant", [0, 30, 31, 32])
+@pytest.mark.parametrize("variant", [0, 30, 31, 32, 10, 11, 12, 13, 14, 15])   # 30-32: forward launches, 10-15: backward item shapes
 def test_correlation_stays_in_bounds(shape, variant):
     from arflow_b200 import _lib
     lib = _lib.load()
