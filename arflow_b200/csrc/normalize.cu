@@ -186,6 +186,100 @@ featnorm_bwd_apply_kernel(const float* __restrict__ f1, const float* __restrict_
     }
 }
 
+// ------------------------------------------------------------------ small maps: one launch ---------------------
+// The coarse pyramid levels (n = C*H*W <= 8 k elements per map and sample; at 24 k one CTA per sample already loses: 41 vs 25 us backward) are pure launch latency for the three-kernel
+// chain above.  Here ONE CTA of 1024 threads owns a sample: pass 1 forms the sums, thread 0 the statistics (same
+// formulas), pass 2 re-reads the maps (a few hundred KB: L1 / L2 hits) and applies them.
+constexpr int kSmallThreads = 1024;
+constexpr long long kSmallMax = 8192;
+
+// sum over the CTA of up to four doubles per thread; result broadcast to every thread through `out`
+template <int K>
+__device__ __forceinline__ void cta_sum_d(double (&v)[K], double (*red)[32], double* out) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if (lane == 0) red[k][w] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double r = 0.0;
+        for (int i = 0; i < kSmallThreads / 32; ++i) r += red[threadIdx.x][i];      // fixed order
+        out[threadIdx.x] = r;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSmallThreads)
+featnorm_fwd_small_kernel(const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ y1,
+                          float* __restrict__ y2, float* __restrict__ stats, long long n) {
+    __shared__ double red[4][32];
+    __shared__ double tot[4];
+    __shared__ float ms[2];
+    const long long base = (long long)blockIdx.x * n;
+    double v[4] = {0, 0, 0, 0};
+    for (long long e = threadIdx.x; e < n; e += kSmallThreads) {
+        const double a = f1[base + e], c = f2[base + e];
+        v[0] += a; v[1] += a * a; v[2] += c; v[3] += c * c;
+    }
+    cta_sum_d<4>(v, red, tot);
+    if (threadIdx.x == 0) {
+        const double m1 = tot[0] / n, m2 = tot[2] / n;
+        const double dof = n > 1 ? (double)(n - 1) : 1.0;
+        double v1 = (tot[1] - n * m1 * m1) / dof, v2 = (tot[3] - n * m2 * m2) / dof;
+        v1 = v1 < 0 ? 0 : v1; v2 = v2 < 0 ? 0 : v2;
+        const float mu = __fdiv_rn(__fadd_rn((float)m1, (float)m2), 2.f);
+        const float var = __fdiv_rn(__fadd_rn((float)v1, (float)v2), 2.f);
+        const float sd = __fsqrt_rn(__fadd_rn(var, 1e-16f));
+        stats[blockIdx.x * 4 + 0] = mu;
+        stats[blockIdx.x * 4 + 1] = sd;
+        stats[blockIdx.x * 4 + 2] = (float)m1;
+        stats[blockIdx.x * 4 + 3] = (float)m2;
+        ms[0] = mu; ms[1] = sd;
+    }
+    __syncthreads();
+    const float mu = ms[0], sd = ms[1];
+    for (long long e = threadIdx.x; e < n; e += kSmallThreads) {
+        y1[base + e] = __fdiv_rn(f1[base + e] - mu, sd);
+        y2[base + e] = __fdiv_rn(f2[base + e] - mu, sd);
+    }
+}
+
+__global__ void __launch_bounds__(kSmallThreads)
+featnorm_bwd_small_kernel(const float* __restrict__ f1, const float* __restrict__ f2, const float* __restrict__ g1,
+                          const float* __restrict__ g2, const float* __restrict__ stats, float* __restrict__ d1,
+                          float* __restrict__ d2, float* __restrict__ coef, long long n) {
+    __shared__ double red[2][32];
+    __shared__ double tot[2];
+    __shared__ float ab[2];
+    const long long base = (long long)blockIdx.x * n;
+    const float mu = __ldg(stats + blockIdx.x * 4), sd = __ldg(stats + blockIdx.x * 4 + 1);
+    const float m1 = __ldg(stats + blockIdx.x * 4 + 2), m2 = __ldg(stats + blockIdx.x * 4 + 3);
+    double v[2] = {0, 0};
+    for (long long e = threadIdx.x; e < n; e += kSmallThreads) {
+        const double ga = g1[base + e], gc = g2[base + e];
+        v[0] += ga + gc;
+        v[1] += ga * (f1[base + e] - mu) + gc * (f2[base + e] - mu);
+    }
+    cta_sum_d<2>(v, red, tot);
+    if (threadIdx.x == 0) {
+        const double s = sd;
+        const double dof = n > 1 ? (double)(n - 1) : 1.0;
+        ab[0] = (float)(-tot[0] / (2.0 * n * s));
+        ab[1] = (float)(-tot[1] / (2.0 * s * s * s * dof));
+        coef[blockIdx.x * 2 + 0] = ab[0];
+        coef[blockIdx.x * 2 + 1] = ab[1];
+    }
+    __syncthreads();
+    const float A = ab[0], Bv = ab[1], inv_s = 1.f / sd;
+    for (long long e = threadIdx.x; e < n; e += kSmallThreads) {
+        if (d1) d1[base + e] = fmaf(g1[base + e], inv_s, fmaf(Bv, f1[base + e] - m1, A));
+        if (d2) d2[base + e] = fmaf(g2[base + e], inv_s, fmaf(Bv, f2[base + e] - m2, A));
+    }
+}
+
 inline int nchunks_n(long long n) { return (int)((n + kNChunk - 1) / kNChunk); }
 inline bool al16(const void* p) { return ((uintptr_t)p % 16) == 0; }
 
@@ -204,6 +298,11 @@ extern "C" int arf_featnorm_fwd(const float* f1, const float* f2, float* y1, flo
     const int nc = nchunks_n(n);
     const int vec = (n % 4 == 0) && al16(f1) && al16(f2) && al16(y1) && al16(y2);
     cudaStream_t st = (cudaStream_t)stream;
+    if (n <= kSmallMax) {
+        featnorm_fwd_small_kernel<<<(unsigned)B, kSmallThreads, 0, st>>>(f1, f2, y1, y2, stats, n);
+        ARF_CHECK_LAUNCH();
+        return ARF_OK;
+    }
     dim3 grid((unsigned)nc, (unsigned)B);
     featnorm_moments_kernel<<<grid, kNThreads, 0, st>>>(f1, f2, (double*)ws, n, vec);
     ARF_CHECK_LAUNCH();
@@ -222,6 +321,11 @@ extern "C" int arf_featnorm_bwd(const float* f1, const float* f2, const float* g
     const int nc = nchunks_n(n);
     const int vec = (n % 4 == 0) && al16(f1) && al16(f2) && al16(g1) && al16(g2) && (!d1 || al16(d1)) && (!d2 || al16(d2));
     cudaStream_t st = (cudaStream_t)stream;
+    if (n <= kSmallMax) {
+        featnorm_bwd_small_kernel<<<(unsigned)B, kSmallThreads, 0, st>>>(f1, f2, g1, g2, stats, d1, d2, coef, n);
+        ARF_CHECK_LAUNCH();
+        return ARF_OK;
+    }
     dim3 grid((unsigned)nc, (unsigned)B);
     featnorm_bwd_reduce_kernel<<<grid, kNThreads, 0, st>>>(f1, f2, g1, g2, stats, (double*)ws, n, vec);
     ARF_CHECK_LAUNCH();

@@ -119,9 +119,10 @@ def test_pad_in_channels():
 
 
 # --------------------------------------------------------------------------- normalize_features (row N1)
-@pytest.mark.parametrize("shape", [(2, 32, 24, 32), (3, 32, 6, 8), (1, 5, 7, 9)])
+@pytest.mark.parametrize("shape", [(2, 32, 24, 32), (3, 32, 6, 8), (1, 5, 7, 9), (2, 32, 48, 64), (2, 32, 32, 33)])
 def test_normalize_features_fused_matches_torch_chain(shape):
-    """arf_featnorm_* against the reference's chain of torch ops (models/uflow_model.py:8-50), values and gradients."""
+    """arf_featnorm_* against the reference's chain of torch ops (models/uflow_model.py:8-50), values and gradients: the
+    single-launch kernels (n <= 8192 elements per map and sample) and the three-kernel chain."""
     from arflow_b200.uflow_model import normalize_features
     gen = torch.Generator().manual_seed(shape[1] + shape[2])
     f1 = (torch.randn(shape, generator=gen) * 0.7 + 0.3).cuda().requires_grad_(True)
