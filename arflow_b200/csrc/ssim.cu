@@ -125,40 +125,43 @@ ssim_coeff_kernel(const float* __restrict__ x, const float* __restrict__ y, cons
     float c_my = gS1 * dS1_dmy + gS2 * (dS2_dsxy * (-s.mx) + dS2_ds * (-2.f * s.my));
     coef[o] = c_mx * inv;
     coef[plane + o] = c_my * inv;
-    coef[2 * plane + o] = gS2 * dS2_ds * inv;      // exx
-    coef[3 * plane + o] = gS2 * dS2_ds * inv;      // eyy
-    coef[4 * plane + o] = gS2 * dS2_dsxy * inv;    // exy
+    coef[2 * plane + o] = gS2 * dS2_ds * inv;      // exx and eyy (the same coefficient)
+    coef[3 * plane + o] = gS2 * dS2_dsxy * inv;    // exy
 }
 
+// grid = (column blocks, rows, planes strided); the (2R+1)^2 window walk is unrolled, four coefficient planes
+// (d / d exx == d / d eyy), 32-bit offsets inside a plane
+template <int R>
 __global__ void __launch_bounds__(256)
 ssim_gather_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ coef,
                    float* __restrict__ gx, float* __restrict__ gy, SsimGeom g) {
     const size_t plane = (size_t)g.planes * g.Ho * g.Wo;
-    const long long total = (long long)g.planes * g.H * g.W;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        int qx = idx % g.W;
-        long long t = idx / g.W;
-        int qy = t % g.H, p = t / g.H;
-        // windows (output pixels) containing input pixel q
-        int oy_lo = g.valid ? qy - 2 * g.r : qy - g.r, oy_hi = g.valid ? qy : qy + g.r;
-        int ox_lo = g.valid ? qx - 2 * g.r : qx - g.r, ox_hi = g.valid ? qx : qx + g.r;
-        oy_lo = max(oy_lo, 0); ox_lo = max(ox_lo, 0);
-        oy_hi = min(oy_hi, g.Ho - 1); ox_hi = min(ox_hi, g.Wo - 1);
-        float a_mx = 0.f, a_my = 0.f, a_xx = 0.f, a_yy = 0.f, a_xy = 0.f;
+    const int qx = blockIdx.x * blockDim.x + threadIdx.x, qy = blockIdx.y;
+    if (qx >= g.W) return;
+    // windows (output pixels) containing input pixel q: centres q-R..q+R (same) or top-left corners q-2R..q (valid)
+    const int oy0 = g.valid ? qy - 2 * R : qy - R, ox0 = g.valid ? qx - 2 * R : qx - R;
+    for (int p = blockIdx.z; p < g.planes; p += gridDim.z) {
         const float* cp = coef + (size_t)p * g.Ho * g.Wo;
-        for (int oy = oy_lo; oy <= oy_hi; ++oy)
-            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-                size_t o = (size_t)oy * g.Wo + ox;
+        float a_mx = 0.f, a_my = 0.f, a_ss = 0.f, a_xy = 0.f;
+#pragma unroll
+        for (int dy = 0; dy <= 2 * R; ++dy) {
+            const int oy = oy0 + dy;
+            if (oy < 0 || oy >= g.Ho) continue;
+#pragma unroll
+            for (int dx = 0; dx <= 2 * R; ++dx) {
+                const int ox = ox0 + dx;
+                if (ox < 0 || ox >= g.Wo) continue;
+                const int o = oy * g.Wo + ox;
                 a_mx += __ldg(cp + o);
                 a_my += __ldg(cp + plane + o);
-                a_xx += __ldg(cp + 2 * plane + o);
-                a_yy += __ldg(cp + 3 * plane + o);
-                a_xy += __ldg(cp + 4 * plane + o);
+                a_ss += __ldg(cp + 2 * plane + o);
+                a_xy += __ldg(cp + 3 * plane + o);
             }
-        float xv = __ldg(x + idx), yv = __ldg(y + idx);
-        if (gx) gx[idx] = a_mx + 2.f * xv * a_xx + yv * a_xy;
-        if (gy) gy[idx] = a_my + 2.f * yv * a_yy + xv * a_xy;
+        }
+        const size_t idx = ((size_t)p * g.H + qy) * g.W + qx;
+        const float xv = __ldg(x + idx), yv = __ldg(y + idx);
+        if (gx) gx[idx] = a_mx + 2.f * xv * a_ss + yv * a_xy;
+        if (gy) gy[idx] = a_my + 2.f * yv * a_ss + xv * a_xy;
     }
 }
 
@@ -213,7 +216,21 @@ extern "C" int arf_ssim_bwd(const float* x, const float* y, const float* g1, con
         default: return ARF_EUNSUPPORTED;
     }
     ARF_CHECK_LAUNCH();
-    ssim_gather_kernel<<<arf_grid_1d(planes * H * W, 256), 256, 0, st>>>(x, y, coef, gx, gy, g);
+    {
+        const int bx = arf_cdiv(W, 256);
+        long long bz = (16LL * ARF_NUM_SMS + (long long)bx * H - 1) / ((long long)bx * H);
+        if (bz > planes) bz = planes;
+        if (bz > 65535) bz = 65535;
+        if (bz < 1) bz = 1;
+        if (H > 65535) return ARF_EINVAL;
+        dim3 grid((unsigned)bx, (unsigned)H, (unsigned)bz);
+        switch (g.r) {
+            case 1: ssim_gather_kernel<1><<<grid, 256, 0, st>>>(x, y, coef, gx, gy, g); break;
+            case 2: ssim_gather_kernel<2><<<grid, 256, 0, st>>>(x, y, coef, gx, gy, g); break;
+            case 3: ssim_gather_kernel<3><<<grid, 256, 0, st>>>(x, y, coef, gx, gy, g); break;
+            default: return ARF_EUNSUPPORTED;
+        }
+    }
     ARF_CHECK_LAUNCH();
     return ARF_OK;
 }
