@@ -278,7 +278,7 @@ def main():
     if args.what in ("loss", "all"):
         # the remaining SURVEY §8(a) rows at the chairs_uflow loss shapes: SSIM (P2/P4), NHWC resampler (W3), masks (M1-M3),
         # smoothness (S1), resize (U1), inverse_diagonal (T4)
-        B, H, W = 8, 384, 512
+        B, H, W = (shapes[0][0], shapes[0][2], shapes[0][3]) if args.shapes else (8, 384, 512)     # full-resolution batch
         px = B * H * W
 
         def mk_ssim(kind):
