@@ -32,6 +32,36 @@ __global__ void inside_mask_kernel(const float* __restrict__ field, float* __res
     }
 }
 
+// four pixels of a row per thread (W % 4 == 0, 16-byte aligned planes): the scalar kernel keeps two 4-byte loads per thread
+// in flight and is latency-bound (102 us for 64 x 320 x 1024 = 2.5 TB/s)
+__global__ void __launch_bounds__(256)
+inside_mask_vec4_kernel(const float* __restrict__ field, float* __restrict__ mask, int B, int H, int W, int kind, int mode) {
+    const unsigned wq = (unsigned)W / 4u;
+    const long long total = (long long)B * H * wq;
+    const size_t hw = (size_t)H * W;
+    const float mw = (float)(W - 1), mh = (float)(H - 1);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int q, i, b;
+        arf_split3(idx, (int)wq, H, q, i, b);
+        const size_t o = (size_t)b * 2 * hw + (size_t)i * W + 4 * (size_t)q;
+        const float4 fx = __ldg(reinterpret_cast<const float4*>(field + o));
+        const float4 fy = __ldg(reinterpret_cast<const float4*>(field + o + hw));
+        float xs[4] = {fx.x, fx.y, fx.z, fx.w}, ys[4] = {fy.x, fy.y, fy.z, fy.w}, m[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float x = xs[t], y = ys[t];
+            if (kind == ARF_FIELD_FLOW) {
+                x = __fadd_rn((float)(4 * q + t), x);
+                y = __fadd_rn((float)i, y);
+            }
+            const bool ok = mode == 0 ? (x >= 0.f && x <= mw && y >= 0.f && y <= mh) : (x > 0.f && x < mw && y > 0.f && y < mh);
+            m[t] = ok ? 1.f : 0.f;
+        }
+        *reinterpret_cast<float4*>(mask + (size_t)b * hw + (size_t)i * W + 4 * (size_t)q) = make_float4(m[0], m[1], m[2], m[3]);
+    }
+}
+
 // compute_range_map (uflow_utils.py:80-160 == warp_utils.py:158-239) and get_corresponding_map
 // (warp_utils.py:26-80): every pixel splats the bilinear weights of its target onto the 4 integer
 // neighbours that lie inside the image.  count must be zero on entry.
@@ -134,6 +164,12 @@ extern "C" int arf_inside_mask(const float* field, float* mask, int B, int H, in
                                void* stream) {
     ARF_REQUIRE(field && mask && B > 0 && H > 0 && W > 0);
     long long total = (long long)B * H * W;
+    if (W % 4 == 0 && (uintptr_t)field % 16 == 0 && (uintptr_t)mask % 16 == 0) {
+        inside_mask_vec4_kernel<<<arf_grid_1d(total / 4, 256, 16), 256, 0, (cudaStream_t)stream>>>(field, mask, B, H, W,
+                                                                                                   field_kind, strict);
+        ARF_CHECK_LAUNCH();
+        return ARF_OK;
+    }
     inside_mask_kernel<<<arf_grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(field, mask, B, H, W, field_kind,
                                                                                    strict ? 1 : 0);
     ARF_CHECK_LAUNCH();

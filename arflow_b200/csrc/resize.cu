@@ -95,30 +95,36 @@ __global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict
     }
 }
 
-// ------------------------------------------------------------------ exact x2 up-sampling (align_corners = False) ---
+// ------------------------------------------------------------------ exact x2 / x4 up-sampling (align_corners = False) ---
 // upsample(flow, is_flow=True) of every pyramid level and the two x2 steps to full resolution (uflow_model.py:220,
-// 343-344) are all this one geometry.  Same arithmetic as the general kernels - the tap indices and weights still come
+// 343-344) are all the x2 geometry, the occlusion mask of the loss (uflow_loss.py:41) is up-sampled x4 (forward only).  Same arithmetic as the general kernels - the tap indices and weights still come
 // from src_index, and the backward adds its taps in the same order, so results are bit-identical - but the work is
 // laid out for the geometry: forward, a thread produces the two outputs above one source pixel from 2 x 3 loads and
 // stores them as one float2 (no per-pixel div / mod); backward, a thread gathers its fixed 4 x 4 candidate window
 // instead of deriving a candidate range with floor / ceil and walking it (the general kernel: ~400 instructions per
 // input pixel, 59 us for 32 planes of 192 x 256 -> 384 x 512; the window form: 16 loads and FMAs).
-__global__ void __launch_bounds__(256) resize_up2_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, ResizeGeom g) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;     // source column; outputs 2k, 2k + 1
+template <int S>     // integer up-sampling factor: a thread writes the S outputs above source column k as one vector
+__global__ void __launch_bounds__(256) resize_ups_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, ResizeGeom g) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int oy = blockIdx.y;
     if (k >= g.Wi) return;
-    int y0, y1, xa0, xa1, xb0, xb1;
-    float hy0, hy1, wa0, wa1, wb0, wb1;
+    int y0, y1, xa[S], xb[S];
+    float hy0, hy1, wa[S], wb[S];
     src_index(oy, g.rh, g.Hi, 0, y0, y1, hy0, hy1);
-    src_index(2 * k, g.rw, g.Wi, 0, xa0, xa1, wa0, wa1);
-    src_index(2 * k + 1, g.rw, g.Wi, 0, xb0, xb1, wb0, wb1);
+#pragma unroll
+    for (int i = 0; i < S; ++i) src_index(S * k + i, g.rw, g.Wi, 0, xa[i], xb[i], wa[i], wb[i]);
     const size_t ip = (size_t)g.Hi * g.Wi, op = (size_t)g.Ho * g.Wo;
     for (unsigned n = blockIdx.z; n < (unsigned)g.N; n += gridDim.z) {
         const float* r0 = in + n * ip + (size_t)y0 * g.Wi;
         const float* r1 = in + n * ip + (size_t)y1 * g.Wi;
-        const float va = hy0 * (wa0 * __ldg(r0 + xa0) + wa1 * __ldg(r0 + xa1)) + hy1 * (wa0 * __ldg(r1 + xa0) + wa1 * __ldg(r1 + xa1));
-        const float vb = hy0 * (wb0 * __ldg(r0 + xb0) + wb1 * __ldg(r0 + xb1)) + hy1 * (wb0 * __ldg(r1 + xb0) + wb1 * __ldg(r1 + xb1));
-        *reinterpret_cast<float2*>(out + n * op + (size_t)oy * g.Wo + 2 * k) = make_float2(va * g.mul, vb * g.mul);
+        float v[S];
+#pragma unroll
+        for (int i = 0; i < S; ++i)
+            v[i] = (hy0 * (wa[i] * __ldg(r0 + xa[i]) + wb[i] * __ldg(r0 + xb[i])) +
+                    hy1 * (wa[i] * __ldg(r1 + xa[i]) + wb[i] * __ldg(r1 + xb[i]))) * g.mul;
+        float* o = out + n * op + (size_t)oy * g.Wo + S * k;
+        if (S == 2) *reinterpret_cast<float2*>(o) = make_float2(v[0], v[1]);
+        else *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
 
@@ -164,10 +170,11 @@ __global__ void __launch_bounds__(256) resize_up2_bwd_kernel(const float* __rest
     }
 }
 
-static inline bool is_up2(const ResizeGeom& g) {
-    return !g.align && g.Ho == 2 * g.Hi && g.Wo == 2 * g.Wi && g.rh == 0.5f && g.rw == 0.5f && g.Ho <= 65535 && g.Hi >= 2 &&
-           g.Wi >= 2;
+static inline bool is_ups(const ResizeGeom& g, int S) {
+    return !g.align && g.Ho == S * g.Hi && g.Wo == S * g.Wi && g.rh == 1.0f / S && g.rw == 1.0f / S && g.Ho <= 65535 &&
+           g.Hi >= 2 && g.Wi >= 2;
 }
+static inline bool is_up2(const ResizeGeom& g) { return is_ups(g, 2); }
 // rows on grid.y, planes strided over grid.z
 static inline dim3 up2_grid(int cols, int rows, long long planes) {
     const long long bx = (cols + 255) / 256;
@@ -208,7 +215,9 @@ extern "C" int arf_resize_bilinear_fwd(const float* in, float* out, long long pl
     int rc = make_geom(g, planes, Hi, Wi, Ho, Wo, rh, rw, mul, align_corners);
     if (rc) return rc;
     if (is_up2(g) && ((uintptr_t)out % 8 == 0))
-        resize_up2_fwd_kernel<<<up2_grid(Wi, Ho, planes), 256, 0, (cudaStream_t)stream>>>(in, out, g);
+        resize_ups_fwd_kernel<2><<<up2_grid(Wi, Ho, planes), 256, 0, (cudaStream_t)stream>>>(in, out, g);
+    else if (is_ups(g, 4) && ((uintptr_t)out % 16 == 0))
+        resize_ups_fwd_kernel<4><<<up2_grid(Wi, Ho, planes), 256, 0, (cudaStream_t)stream>>>(in, out, g);
     else
         resize_fwd_kernel<<<resize_grid((long long)Ho * Wo, planes), 256, 0, (cudaStream_t)stream>>>(in, out, g);
     ARF_CHECK_LAUNCH();

@@ -37,6 +37,25 @@ def test_masks_golden():
     assert torch.equal(wu.get_occu_mask_bidirection(flow * 0.3, flow_b * 0.3).cpu(), g["occ_bi_out0_f32"])
 
 
+@pytest.mark.parametrize("shape", [(2, 24, 32), (3, 17, 20), (1, 9, 13), (2, 96, 128)])
+def test_inside_masks_vs_torch(shape):
+    """mask_invalid / border_mask for widths that take the four-pixels-per-thread kernel (W % 4 == 0) and the scalar one:
+    bit-equal to the reference's comparisons on coordinates built by the same single fp32 add."""
+    from arflow_b200 import uflow_utils as uu
+    from arflow_b200 import warp_utils as wu
+    B, H, W = shape
+    gen = torch.Generator().manual_seed(B * H + W)
+    flow = (torch.randn(B, 2, H, W, generator=gen) * 6).cuda()
+    flow[:, :, 0, 0] = 0.0                      # a coordinate exactly on the border
+    flow[:, 0, -1, -1] = 0.0
+    yy, xx = torch.meshgrid(torch.arange(H, device="cuda", dtype=torch.float32), torch.arange(W, device="cuda", dtype=torch.float32), indexing="ij")
+    x, y = xx + flow[:, 0], yy + flow[:, 1]
+    ref0 = ((x >= 0) & (x <= W - 1) & (y >= 0) & (y <= H - 1)).float().unsqueeze(1)
+    ref1 = ((x > 0) & (x < W - 1) & (y > 0) & (y < H - 1)).float().unsqueeze(1)
+    assert torch.equal(uu.mask_invalid_flow(flow), ref0)
+    assert torch.equal(wu.border_mask(flow), ref1)
+
+
 def test_resize_golden():
     from arflow_b200 import uflow_utils as uu
     g = load_golden("resize")
