@@ -107,34 +107,6 @@ __device__ __forceinline__ void pixel_coords(const float* __restrict__ field, co
     Y = source_index(py, g.nH1, g.Hs, g.pad_mode, g.align, dY);
 }
 
-// Bilinear tap geometry of one output pixel (ATen grid_sampler_2d): weights already zeroed for taps
-// outside the source, offsets clamped so every load is legal.
-struct Taps {
-    size_t o[4];       // nw, ne, sw, se element offsets inside one source plane
-    float w[4];        // matching weights (0 for out-of-range taps)
-    float fxe, fxw, fys, fyn;
-    bool in[4];
-};
-
-__device__ __forceinline__ void make_taps(float X, float Y, const WarpGeom& g, Taps& t) {
-    float xf = floorf(X), yf = floorf(Y);
-    int xw = (int)xf, yn = (int)yf, xe = xw + 1, ys = yn + 1;
-    t.fxe = (float)xe - X; t.fxw = X - (float)xw; t.fys = (float)ys - Y; t.fyn = Y - (float)yn;
-    bool inw = xw >= 0 && xw < g.Ws, ine = xe >= 0 && xe < g.Ws;
-    bool inn = yn >= 0 && yn < g.Hs, ins = ys >= 0 && ys < g.Hs;
-    t.in[0] = inn && inw; t.in[1] = inn && ine; t.in[2] = ins && inw; t.in[3] = ins && ine;
-    int xwc = min(max(xw, 0), g.Ws - 1), xec = min(max(xe, 0), g.Ws - 1);
-    int ync = min(max(yn, 0), g.Hs - 1), ysc = min(max(ys, 0), g.Hs - 1);
-    t.o[0] = (size_t)ync * g.Ws + xwc; t.o[1] = (size_t)ync * g.Ws + xec;
-    t.o[2] = (size_t)ysc * g.Ws + xwc; t.o[3] = (size_t)ysc * g.Ws + xec;
-    t.w[0] = t.in[0] ? t.fxe * t.fys : 0.f;
-    t.w[1] = t.in[1] ? t.fxw * t.fys : 0.f;
-    t.w[2] = t.in[2] ? t.fxe * t.fyn : 0.f;
-    t.w[3] = t.in[3] ? t.fxw * t.fyn : 0.f;
-}
-
-constexpr int kCU = 4;   // channels whose loads are issued together
-
 __device__ __forceinline__ float ldg_at(unsigned long long byte_addr) {
     return __ldg(reinterpret_cast<const float*>(byte_addr));
 }
