@@ -4,7 +4,7 @@ Data-parallel modes (world_size > 1), `allreduce=`:
   * "peer" (default on CUDA): gradients live in one flat buffer allocated by arflow_b200.comm.PeerAllReduce; a bucket
     is all-reduced by ONE kernel over NVLink peer memory (csrc/comm.cu) on a side stream as soon as its last gradient
     has been written, overlapping the rest of backward.  The kernel is an ordinary launch, so the whole step — forward,
-    loss, backward, the three bucket all-reduces, Adam — is captured in ONE CUDA graph; the batch-global census
+    loss, backward, the bucket all-reduces, Adam — is captured in ONE CUDA graph; the batch-global census
     normaliser (a 16-byte all-reduce inside the forward pass) rides the same mechanism.
   * "nccl": the same buckets through torch.distributed.  Eager: overlapped on a side stream.  With use_graph:
     forward+backward are one captured graph, the all-reduce of the whole flat buffer is ONE eager NCCL call between
