@@ -18,7 +18,7 @@ def main(src, dst):
         rows.append((len(rows), r[kn].replace(",", ";"), us))
     with open(dst, "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off python bench.py --profile-step\n")
-        f.write("# one eager chairs_uflow train step (B=8, 384x512, channels-last conv stacks) on B200, end of round 1; "
+        f.write("# one eager chairs_uflow train step (B=8, 384x512, channels-last conv stacks) on B200, end of the round named in the file; "
                 "per-launch times are cold-cache and serialised (compare shares)\n")
         f.write("id,kernel,duration_us\n")
         for i, k, us in rows:
