@@ -701,7 +701,7 @@ template <int R>
 int launch_bwd_sym(const float* im_a, const float* im_b, const float* ghamming, const float* hamming, const float* mask,
                    const float* sums, const float* gloss, float* g_a, float* g_b, int B, int H, int W, int groups,
                    float scale, float eps, float q, cudaStream_t st) {
-    const int hs = sym_strip_height(B, H, W, SymGeo<R>::kOwn, R, 3);
+    const int hs = sym_strip_height(B, H, W, SymGeo<R>::kOwn, R, 4);
     const int nsx = arf_cdiv(W, SymGeo<R>::kOwn), nsy = arf_cdiv(H, hs);
     const long long nstrips = (long long)nsx * nsy * B;
     const long long nblk = (nstrips + kSymWarps - 1) / kSymWarps;
