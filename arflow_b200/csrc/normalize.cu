@@ -14,7 +14,7 @@
 namespace {
 
 constexpr int kNThreads = 256;
-constexpr int kNChunk = 8192;      // elements of one sample handled by one CTA
+constexpr int kNChunk = 8192;      // elements of one sample handled by one CTA (16x32x96x128 fwd / bwd: 4096 -> 41 / 52 us, 8192 -> 37 / 51, 16384 -> 36 / 57)
 
 __device__ __forceinline__ double block_sum_d(double v, double* red) {
 #pragma unroll
